@@ -1,0 +1,92 @@
+/* voldor_b200 — C ABI of the B200-native VOLDOR EM hot path.
+ *
+ * Plain-C aliases (prefix vb_) of the C++-linkage entry points in gpu_kernels.h / py_export.h, for FFI users
+ * (ctypes, cgo, JNI, ...).  Each cites the reference interface it replaces; semantics are identical to the
+ * C++ symbols (host pointers, NULL = cached / skip, int return code).  `bool` parameters are `int` here and
+ * the C++ reference-to-int output of py_voldor_wrapper is a pointer.
+ */
+#ifndef VOLDOR_B200_H_
+#define VOLDOR_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* reference: gpu-kernels/gpu_kernels.h:11-15 (meanshift.cu:34-150) */
+int vb_meanshift_gpu(float* h_space, float kernel_var, float* h_io_mean, float* h_o_confidence, int* used_iters,
+                     int use_external_init_mean, int N, int dims, float epsilon, int max_iters,
+                     int max_init_trials, float good_init_confidence);
+
+/* reference: gpu-kernels/gpu_kernels.h:17-22 (fit_robust_gaussian.cu:101-286) */
+int vb_fit_robust_gaussian(float* h_space, float* h_io_mean, float* h_io_covar, float trunc_sigma,
+                           float covar_reg_lambda, float* h_o_density, int* used_iters, int N, int dims,
+                           float epsilon, int max_iters);
+
+/* reference: gpu-kernels/gpu_kernels.h:24-35 (collect_p3p_instances.cu:147-250) */
+int vb_collect_p3p_instances(float** h_flows, float** h_rigidnesses, float* h_depth, float* h_K, float** h_Rs,
+                             float** h_ts, float* h_o_p2_map, float* h_o_p3_map, int N, int w, int h,
+                             int active_idx, float rigidness_thresh, float rigidness_sum_thresh,
+                             float sample_min_depth, float sample_max_depth, int max_trace_on_flow);
+
+/* reference: gpu-kernels/gpu_kernels.h:37-39 (solve_batch_ap3p.cu:387-437) */
+int vb_solve_batch_p3p_ap3p_gpu(float* h_p3s, float* h_p2s, float* h_o_rvecs, float* h_o_tvecs, float* h_K,
+                                int N_pts, int N_poses);
+
+/* reference: gpu-kernels/gpu_kernels.h:40-42 (solve_batch_lambdatwist.cu:51-102) */
+int vb_solve_batch_p3p_lambdatwist_gpu(float* h_p3s, float* h_p2s, float* h_o_rvecs, float* h_o_tvecs, float* h_K,
+                                       int N_pts, int N_poses);
+
+/* reference: gpu-kernels/gpu_kernels.h:44-58 (optimize_depth.cu:293-520) */
+int vb_optimize_depth_gpu(float** h_flows, float** h_rigidnesses, float** h_o_rigidnesses, float** h_depth_priors,
+                          float** h_depth_prior_pconfs, float** h_depth_prior_confs, float** h_o_depth_prior_confs,
+                          float* h_depth, float* h_o_depth, float* h_K, float** h_Rs, float** h_ts, float** h_dp_Rs,
+                          float** h_dp_ts, float abs_resize_factor, int N, int N_dp, int w, int h, float basefocal,
+                          int n_rand_samples, int global_prop_step, int local_prop_width, float lambda, float omega,
+                          float disp_delta, float delta, int fb_smooth, float s0_ems_prob, float no_change_prob,
+                          float range_factor, int update_rigidness_only);
+
+/* reference: gpu-kernels/gpu_kernels.h:60-66 (align_frame.cu:512-554) */
+int vb_align_frame_init_gpu(float** h_images, float** h_depths, float** h_weights, float* h_K, float vbf, float crw,
+                            int N, int w, int h);
+
+/* reference: gpu-kernels/gpu_kernels.h:68-74 (align_frame.cu:414-510) */
+int vb_align_frame_eval_gpu(int ref_fid, int tar_fid, const float* h_params_ref, const float* h_params_tar,
+                            float* h_o_residual, float* h_o_jacobian, int apply_weights);
+
+/* reference: gpu-kernels/gblur.h:6 (gblur.cu:47-72; device-to-device in the reference, host buffers here).
+ * src/dst: [depth][h][w] float, ksize odd. */
+int vb_gblur_gpu(const float* h_src, float* h_dst, int w, int h, int depth, float sigma, int ksize);
+
+/* reference: voldor/py_export.h:3-11 (py_export.cpp:5-79) — one VO window through the device-resident pipeline */
+int vb_py_voldor_wrapper(const float* flows, const float* disparity, const float* disparity_pconf,
+                         const float* depth_priors, const float* depth_prior_poses, const float* depth_prior_pconfs,
+                         float fx, float fy, float cx, float cy, float basefocal, int N, int N_dp, int w, int h,
+                         const char* config, int* n_registered, float* poses, float* poses_covar, float* depth,
+                         float* depth_conf);
+
+/* ---- additions that have no counterpart in the reference ---- */
+
+/* Monocular bootstrap injection: when set (valid != 0), the next windows that have no depth prior start from
+ * this pose (R row-major 3x3, t) and depth map instead of the essential-matrix bootstrap
+ * (reference: voldor/voldor.cpp:151-162, geometry.cpp:267-332).  Used by the measurement harness so every
+ * series starts from identical state. */
+int vb_set_bootstrap_override(int valid, const float* R9, const float* t3, const float* depth, int w, int h);
+
+/* Same window call, also reporting the number of EM iterations executed (VOLDOR::solve's return value,
+ * voldor/voldor.cpp:148) and per-stage device/host time in ms: stats[0]=total, [1]=cameras, [2]=depth, [3]=io. */
+int vb_py_voldor_wrapper_ex(const float* flows, const float* disparity, const float* disparity_pconf,
+                            const float* depth_priors, const float* depth_prior_poses,
+                            const float* depth_prior_pconfs, float fx, float fy, float cx, float cy, float basefocal,
+                            int N, int N_dp, int w, int h, const char* config, int* n_registered, float* poses,
+                            float* poses_covar, float* depth, float* depth_conf, int* iters_run, float* stats);
+
+/* Select the CUDA device used by this process' state (default: current device). */
+int vb_set_device(int device);
+
+/* Library self-description: returns a static string "voldor_b200 <version> sm_100a". */
+const char* vb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOLDOR_B200_H_ */

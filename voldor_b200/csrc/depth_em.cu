@@ -1,0 +1,583 @@
+// Depth M-step / rigidness E-step kernels for sm_100a.
+//
+// What the reference does (gpu-kernels/optimize_depth.cu:462-494, fb_smooth.h:72-107) in 26+ launches over
+// texture-backed GMats, restructured for B200:
+//   * forward-backward smoothing: row chains are walked from shared-memory tiles that are loaded/stored
+//     fully coalesced (one warp = 32 rows, 32-column tiles, register prefetch of the next tile), both
+//     directions of a pass run in one launch; column chains are naturally coalesced.
+//   * cost map + all `n_rand_samples` random candidates are ONE kernel: depth, best cost and the XORWOW
+//     state live in registers for the whole search; the reference reloads/stores the 48-byte curandState
+//     and the cost map in each of its 1+10 launches (optimize_depth.cu:269-284,472-478).
+//   * global propagation with step>1 has no intra-pass dependency (writes x≡1 mod step, reads x-1), so it
+//     runs on (w/step)*h lanes instead of the reference's h (or w) threads (optimize_depth.cu:209-235).
+//   * local propagation keeps its sequential 31-long chains (optimize_depth.cu:237-267).
+// Candidate costs use explicitly rounded FP32 arithmetic in the reference's evaluation order
+// (residual_model.cuh) because the argmin over candidates must reproduce the reference's decisions.
+#include "depth_em.cuh"
+#include "residual_model.cuh"
+#include "geometry.cuh"
+#include <cmath>
+#include <curand_kernel.h>
+
+namespace vb {
+
+namespace {
+
+constexpr unsigned long long kRandSeed = 233;  // reference: gpu-kernels/utils.h:18
+constexpr float kMaximumDepth = 1e5f;          // reference: optimize_depth.cu:15
+
+// Kernel-side view of the window state.
+struct DepthView {
+    int N, N_dp, w, h;
+    int pitch;      // elements, for depth/cost/rig/rng planes
+    size_t plane;   // pitch*h
+    float abs_rf, basefocal, lambda, omega, delta, disp_delta, range_factor;
+    cudaTextureObject_t flows_tex, dp_tex, dp_pconf_tex, dp_conf_tex;
+    float* rig;
+    float* depth;
+    float* cost;
+    uint32_t* rng;
+    float* dp_conf;
+    int dp_conf_pitch;      // elements
+    size_t dp_conf_plane;   // elements per layer
+};
+
+// ------------------------------------------------------------------------------------------------
+// cost of hypothesising `depth` at pixel (px,py)   (reference: optimize_depth.cu:140-198)
+// ------------------------------------------------------------------------------------------------
+__device__ float pixel_cost(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC, int px, int py,
+                            float depth) {
+    float cost_sum = 0.f;
+    float weight_sum = 0.f;
+    const float fpx = (float)px, fpy = (float)py;
+    const float fw = (float)A.w, fh = (float)A.h;
+
+    float ox, oy, oz;
+    backproject(C, fpx, fpy, depth, ox, oy, oz);
+    float px1 = fpx, py1 = fpy;
+    const float* wgt_ptr = A.rig + (size_t)py * A.pitch + px;
+
+    for (int f = 0; f < A.N; f++) {
+        float px2, py2;
+        rigid_move(C.R[f], C.t[f], ox, oy, oz);
+        project(C, ox, oy, oz, px2, py2);
+        if (oz > 0 && px1 >= 0 && px1 < fw && py1 >= 0 && py1 < fh) {
+            const float2 obs = fetch_stack<float2>(A.flows_tex, px1, py1, f, A.h);
+            const float rfx = f_sub(px2, px1), rfy = f_sub(py2, py1);
+            px1 = px2, py1 = py2;  // stale when the branch is not taken
+            const float wgt = wgt_ptr[(size_t)f * A.plane];
+            const float r = flow_rigidness(rfx, rfy, obs.x, obs.y, A.lambda, A.abs_rf);
+            cost_sum = f_fma(-wgt, logf(r), cost_sum);
+            weight_sum = f_add(weight_sum, wgt);
+        }
+    }
+
+    for (int f = 0; f < A.N_dp; f++) {
+        backproject(C, fpx, fpy, depth, ox, oy, oz);
+        rigid_move(PC.R[f], PC.t[f], ox, oy, oz);
+        project(C, ox, oy, oz, px1, py1);
+        if (oz > 0 && px1 >= 0 && px1 < fw && py1 >= 0 && py1 < fh) {
+            const float target_depth = fetch_stack<float>(A.dp_tex, px1, py1, f, A.h);
+            const float target_pconf = fetch_stack<float>(A.dp_pconf_tex, px1, py1, f, A.h);
+            const float target_conf = fetch_stack<float>(A.dp_conf_tex, px1, py1, f, A.h);
+            if (target_depth > 0) {
+                // prior 0 is the disparity prior when the caller passes disp_delta > 0
+                const float scale = (A.disp_delta > 0 && f == 0) ? A.disp_delta : A.delta;
+                const float wgt = f_mul(f_mul(target_pconf, target_conf), scale);
+                const float r = depth_rigidness(oz, target_depth, A.basefocal, A.omega, A.abs_rf);
+                cost_sum = f_fma(-wgt, logf(r), cost_sum);
+                weight_sum = f_add(weight_sum, wgt);
+            }
+        }
+    }
+
+    if (weight_sum == 0) return INFINITY;
+    return f_div(cost_sum, fmaxf(weight_sum, FLT_EPSILON));
+}
+
+__device__ __forceinline__ void try_candidate(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC, int x,
+                                              int y, float cand) {
+    const size_t idx = (size_t)y * A.pitch + x;
+    const float c = pixel_cost(A, C, PC, x, y, cand);
+    if (c < A.cost[idx]) {  // strict '<' (reference: optimize_depth.cu:201-207)
+        A.depth[idx] = cand;
+        A.cost[idx] = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// XORWOW (Marsaglia) stream per pixel, bit-compatible with cuRAND's curand_init(seed, subsequence, 0):
+// state words are produced by curand_init itself, the step below is the published recurrence
+// (x ^= x>>2; ... ; d += 362437) and the uniform mapping is cuRAND's (0,1] = u32*2^-32 + 2^-33.
+// ------------------------------------------------------------------------------------------------
+struct Xorwow {
+    uint32_t d, v0, v1, v2, v3, v4;
+};
+__device__ __forceinline__ float xorwow_uniform(Xorwow& s) {
+    const uint32_t t = s.v0 ^ (s.v0 >> 2);
+    s.v0 = s.v1, s.v1 = s.v2, s.v2 = s.v3, s.v3 = s.v4;
+    s.v4 = (s.v4 ^ (s.v4 << 4)) ^ (t ^ (t << 1));
+    s.d += 362437u;
+    const uint32_t r = s.v4 + s.d;
+    return f_fma((float)r, 2.3283064365386963e-10f, 2.3283064365386963e-10f / 2.0f);
+}
+
+__global__ void k_seed_rng(uint32_t* rng, int w, int h, int pitch, size_t plane) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    curandStateXORWOW_t st;
+    curand_init(kRandSeed, (unsigned long long)(y * w + x), 0, &st);  // reference: optimize_depth.cu:286-291
+    const size_t idx = (size_t)y * pitch + x;
+    rng[idx] = st.d;
+    rng[idx + plane] = st.v[0];
+    rng[idx + 2 * plane] = st.v[1];
+    rng[idx + 3 * plane] = st.v[2];
+    rng[idx + 4 * plane] = st.v[3];
+    rng[idx + 5 * plane] = st.v[4];
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused: cost of the current depth + n_rand random candidates   (reference: optimize_depth.cu:269-284)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_cost_and_random_search(const DepthView A, const __grid_constant__ CamBlock C,
+                             const __grid_constant__ PriorCamBlock PC, int n_rand) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= A.w || y >= A.h) return;
+    const size_t idx = (size_t)y * A.pitch + x;
+
+    // it == -1 evaluates the current depth (the reference's compute_cost_map), it >= 0 the random draws
+    Xorwow s = {0, 0, 0, 0, 0, 0};
+    if (n_rand > 0) {
+        s.d = A.rng[idx];
+        s.v0 = A.rng[idx + A.plane];
+        s.v1 = A.rng[idx + 2 * A.plane];
+        s.v2 = A.rng[idx + 3 * A.plane];
+        s.v3 = A.rng[idx + 4 * A.plane];
+        s.v4 = A.rng[idx + 5 * A.plane];
+    }
+    float best_depth = A.depth[idx];
+    float best_cost = 0.f;
+    for (int it = -1; it < n_rand; it++) {
+        float cand = best_depth;
+        if (it >= 0) {
+            const float u = xorwow_uniform(s);
+            // d = 1/(range_factor*U + 1/MAXIMUM_DEPTH)   (reference: optimize_depth.cu:273)
+            cand = __frcp_rn(f_fma(A.range_factor, u, 1.0f / kMaximumDepth));
+        }
+        const float c = pixel_cost(A, C, PC, x, y, cand);
+        if (it < 0 || c < best_cost) {
+            best_depth = cand;
+            best_cost = c;
+        }
+    }
+    if (n_rand > 0) {
+        A.rng[idx] = s.d;
+        A.rng[idx + A.plane] = s.v0;
+        A.rng[idx + 2 * A.plane] = s.v1;
+        A.rng[idx + 3 * A.plane] = s.v2;
+        A.rng[idx + 4 * A.plane] = s.v3;
+        A.rng[idx + 5 * A.plane] = s.v4;
+    }
+    A.depth[idx] = best_depth;
+    A.cost[idx] = best_cost;
+}
+
+// ------------------------------------------------------------------------------------------------
+// global propagation, step > 1: every evaluation of one direction is independent
+//   L2R: x = 1, 1+step, ...   takes depth(x-1)        R2L: x = w-2, w-2-step, ... takes depth(x+1)
+//   T2B: y = 1, 1+step, ...   takes depth(y-1)        B2T: y = h-2, ...           takes depth(y+1)
+// (reference: optimize_depth.cu:209-235)
+// ------------------------------------------------------------------------------------------------
+enum { DIR_L2R = 0, DIR_T2B = 1, DIR_R2L = 2, DIR_B2T = 3 };
+
+template <int DIR>
+__global__ void __launch_bounds__(128)
+    k_global_propagation(const DepthView A, const __grid_constant__ CamBlock C,
+                         const __grid_constant__ PriorCamBlock PC, int step) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;  // index along the strided axis
+    const int o = blockIdx.y * blockDim.y + threadIdx.y;  // index along the other axis
+    int x, y, sx, sy;
+    if (DIR == DIR_L2R) {
+        x = 1 + k * step, y = o, sx = x - 1, sy = y;
+    } else if (DIR == DIR_R2L) {
+        x = A.w - 2 - k * step, y = o, sx = x + 1, sy = y;
+    } else if (DIR == DIR_T2B) {
+        x = o, y = 1 + k * step, sx = x, sy = y - 1;
+    } else {
+        x = o, y = A.h - 2 - k * step, sx = x, sy = y + 1;
+    }
+    if (x < 0 || y < 0 || x >= A.w || y >= A.h) return;
+    try_candidate(A, C, PC, x, y, A.depth[(size_t)sy * A.pitch + sx]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// local propagation: sequential chain inside each `width`-pixel segment (reference: optimize_depth.cu:237-267)
+// thread (seg, o): seg = segment index along the propagation axis, o = index along the other axis.
+// Also serves global propagation with step == 1 (one segment = the whole row/column).
+// ------------------------------------------------------------------------------------------------
+template <int DIR>
+__global__ void __launch_bounds__(128)
+    k_local_propagation(const DepthView A, const __grid_constant__ CamBlock C,
+                        const __grid_constant__ PriorCamBlock PC, int width) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int seg = blockIdx.y * blockDim.y + threadIdx.y;
+    if (DIR == DIR_L2R) {
+        if (o >= A.h) return;
+        const int p0 = seg * width;
+        if (p0 >= A.w) return;
+        const int lo = max(1, p0 + 1), hi = min(A.w, p0 + width);
+        for (int x = lo; x < hi; x++) try_candidate(A, C, PC, x, o, A.depth[(size_t)o * A.pitch + x - 1]);
+    } else if (DIR == DIR_R2L) {
+        if (o >= A.h) return;
+        const int p0 = seg * width;
+        if (p0 >= A.w) return;
+        for (int x = min(A.w - 2, p0 + width - 2); x >= max(0, p0); x--)
+            try_candidate(A, C, PC, x, o, A.depth[(size_t)o * A.pitch + x + 1]);
+    } else if (DIR == DIR_T2B) {
+        if (o >= A.w) return;
+        const int p0 = seg * width;
+        if (p0 >= A.h) return;
+        const int lo = max(1, p0 + 1), hi = min(A.h, p0 + width);
+        for (int y = lo; y < hi; y++) try_candidate(A, C, PC, o, y, A.depth[(size_t)(y - 1) * A.pitch + o]);
+    } else {
+        if (o >= A.w) return;
+        const int p0 = seg * width;
+        if (p0 >= A.h) return;
+        for (int y = min(A.h - 2, p0 + width - 2); y >= max(0, p0); y--)
+            try_candidate(A, C, PC, o, y, A.depth[(size_t)(y + 1) * A.pitch + o]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// E-step: rigidness of every flow and confidence of every prior at the current depth
+// (reference: optimize_depth.cu:84-138)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_update_rigidness(const DepthView A, const __grid_constant__ CamBlock C,
+                       const __grid_constant__ PriorCamBlock PC) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= A.w || y >= A.h) return;
+    const size_t idx = (size_t)y * A.pitch + x;
+    const float fpx = (float)x, fpy = (float)y;
+    const float fw = (float)A.w, fh = (float)A.h;
+    const float depth = A.depth[idx];
+
+    float ox, oy, oz;
+    backproject(C, fpx, fpy, depth, ox, oy, oz);
+    float px1 = fpx, py1 = fpy;
+    for (int f = 0; f < A.N; f++) {
+        float px2, py2;
+        rigid_move(C.R[f], C.t[f], ox, oy, oz);
+        project(C, ox, oy, oz, px2, py2);
+        float r = 0.f;
+        if (oz > 0 && px1 >= 0 && px1 < fw && py1 >= 0 && py1 < fh) {
+            const float2 obs = fetch_stack<float2>(A.flows_tex, px1, py1, f, A.h);
+            const float rfx = f_sub(px2, px1), rfy = f_sub(py2, py1);
+            px1 = px2, py1 = py2;
+            r = flow_rigidness(rfx, rfy, obs.x, obs.y, A.lambda, A.abs_rf);
+        }
+        A.rig[idx + (size_t)f * A.plane] = r;
+    }
+
+    for (int f = 0; f < A.N_dp; f++) {
+        backproject(C, fpx, fpy, depth, ox, oy, oz);
+        rigid_move(PC.R[f], PC.t[f], ox, oy, oz);
+        project(C, ox, oy, oz, px1, py1);
+        float* conf = A.dp_conf + (size_t)f * A.dp_conf_plane + (size_t)y * A.dp_conf_pitch + x;
+        if (oz > 0 && px1 >= 0 && px1 < fw && py1 >= 0 && py1 < fh) {
+            const float target_depth = fetch_stack<float>(A.dp_tex, px1, py1, f, A.h);
+            // confidence is left untouched where the prior has no depth
+            if (target_depth > 0) *conf = depth_rigidness(oz, target_depth, A.basefocal, A.omega, A.abs_rf);
+        } else {
+            *conf = 0.f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward-backward smoothing of a stack of probability maps (2-state HMM along rows, then columns)
+// (reference: fb_smooth.h:29-69).  Rounding points follow the reference build.
+// ------------------------------------------------------------------------------------------------
+struct HmmConst {
+    float nc, one_m_nc, s0e;
+};
+__device__ __forceinline__ float hmm_forward(float p, float e, const HmmConst& k) {
+    const float om = f_sub(1.f, p);
+    const float u0 = f_fma(k.one_m_nc, p, f_mul(k.nc, om));
+    const float u1 = f_fma(k.nc, p, f_mul(k.one_m_nc, om));
+    const float s1 = f_mul(u1, e);
+    return f_div(s1, f_fma(k.s0e, u0, s1));
+}
+__device__ __forceinline__ float hmm_backward(float p, float e, const HmmConst& k) {
+    const float pe = f_mul(p, e);
+    const float om = f_sub(1.f, p);
+    const float s0 = f_fma(k.s0e, f_mul(k.nc, om), f_mul(k.one_m_nc, pe));
+    const float s1 = f_fma(k.s0e, f_mul(k.one_m_nc, om), f_mul(k.nc, pe));
+    return f_div(s1, f_add(s0, s1));
+}
+__device__ __forceinline__ float hmm_posterior(float fwd, float bwd) {
+    const float s1 = f_mul(bwd, fwd);
+    return f_div(s1, f_fma(f_sub(1.f, fwd), f_sub(1.f, bwd), s1));
+}
+
+struct StackView {
+    float* base;
+    int pitch;      // elements
+    size_t plane;   // elements
+};
+
+// rows: grid (ceil(h/32), layers, 2 directions), block 32.  Lane l owns row y0+l; 32x32 tiles are staged
+// through shared memory so global traffic is 128-byte coalesced and the dependent chain reads smem.
+__global__ void __launch_bounds__(32)
+    k_fb_rows(StackView E, StackView F, StackView B, int w, int h, HmmConst k) {
+    __shared__ float tin[32][33];
+    __shared__ float tout[32][33];
+    const int lane = threadIdx.x;
+    const int y0 = blockIdx.x * 32;
+    const int layer = blockIdx.y;
+    const bool fwd = blockIdx.z == 0;
+    const float* e = E.base + (size_t)layer * E.plane;
+    float* out = (fwd ? F.base + (size_t)layer * F.plane : B.base + (size_t)layer * B.plane);
+    const int out_pitch = fwd ? F.pitch : B.pitch;
+    const int T = VB_DIV_CEIL(w, 32);
+    const int rows = min(32, h - y0);
+    const int y = y0 + lane;
+
+    float nxt[32];
+    {
+        const int x0 = (fwd ? 0 : T - 1) * 32;
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+            nxt[r] = (r < rows && x0 + lane < w) ? e[(size_t)(y0 + r) * E.pitch + x0 + lane] : 0.f;
+    }
+    float p = 0.f;
+    if (y < h) p = e[(size_t)y * E.pitch + (fwd ? 0 : w - 1)];
+
+    for (int t = 0; t < T; t++) {
+        const int x0 = (fwd ? t : T - 1 - t) * 32;
+#pragma unroll
+        for (int r = 0; r < 32; r++) tin[r][lane] = nxt[r];
+        __syncwarp();
+        if (t + 1 < T) {
+            const int xn = (fwd ? t + 1 : T - 2 - t) * 32;
+#pragma unroll
+            for (int r = 0; r < 32; r++)
+                nxt[r] = (r < rows && xn + lane < w) ? e[(size_t)(y0 + r) * E.pitch + xn + lane] : 0.f;
+        }
+        if (y < h) {
+            const int cols = min(32, w - x0);
+            if (fwd) {
+                for (int i = 0; i < cols; i++) {
+                    p = hmm_forward(p, tin[lane][i], k);
+                    tout[lane][i] = p;
+                }
+            } else {
+                for (int i = cols - 1; i >= 0; i--) {
+                    p = hmm_backward(p, tin[lane][i], k);
+                    tout[lane][i] = p;
+                }
+            }
+        }
+        __syncwarp();
+        if (x0 + lane < w) {
+            for (int r = 0; r < rows; r++) out[(size_t)(y0 + r) * out_pitch + x0 + lane] = tout[r][lane];
+        }
+        __syncwarp();
+    }
+}
+
+// columns: thread per column, grid (ceil(w/128), layers, 2 directions)
+__global__ void __launch_bounds__(128)
+    k_fb_cols(StackView E, StackView F, StackView B, int w, int h, HmmConst k) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    const int layer = blockIdx.y;
+    const bool fwd = blockIdx.z == 0;
+    const float* __restrict__ e = E.base + (size_t)layer * E.plane + x;
+    float* __restrict__ out = (fwd ? F.base + (size_t)layer * F.plane : B.base + (size_t)layer * B.plane) + x;
+    const int out_pitch = fwd ? F.pitch : B.pitch;
+    constexpr int U = 8;
+    if (fwd) {
+        float p = e[0];
+        for (int y = 0; y < h; y += U) {
+            float ev[U];
+#pragma unroll
+            for (int j = 0; j < U; j++) ev[j] = (y + j < h) ? e[(size_t)(y + j) * E.pitch] : 0.f;
+#pragma unroll
+            for (int j = 0; j < U; j++)
+                if (y + j < h) {
+                    p = hmm_forward(p, ev[j], k);
+                    out[(size_t)(y + j) * out_pitch] = p;
+                }
+        }
+    } else {
+        float p = e[(size_t)(h - 1) * E.pitch];
+        for (int y = h - 1; y >= 0; y -= U) {
+            float ev[U];
+#pragma unroll
+            for (int j = 0; j < U; j++) ev[j] = (y - j >= 0) ? e[(size_t)(y - j) * E.pitch] : 0.f;
+#pragma unroll
+            for (int j = 0; j < U; j++)
+                if (y - j >= 0) {
+                    p = hmm_backward(p, ev[j], k);
+                    out[(size_t)(y - j) * out_pitch] = p;
+                }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fb_posterior(StackView E, StackView F, StackView B, int w, int h) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int layer = blockIdx.z;
+    if (x >= w || y >= h) return;
+    const float f = F.base[(size_t)layer * F.plane + (size_t)y * F.pitch + x];
+    const float b = B.base[(size_t)layer * B.plane + (size_t)y * B.pitch + x];
+    E.base[(size_t)layer * E.plane + (size_t)y * E.pitch + x] = hmm_posterior(f, b);
+}
+
+void fb_smooth_stack(StackView E, StackView F, StackView B, int layers, int w, int h, float s0_ems_prob,
+                     float no_change_prob, cudaStream_t s) {
+    HmmConst k;
+    k.nc = no_change_prob;
+    k.one_m_nc = 1.f - no_change_prob;
+    k.s0e = s0_ems_prob;
+    const dim3 pb(32, 8), pg(VB_DIV_CEIL(w, 32), VB_DIV_CEIL(h, 8), layers);
+    k_fb_rows<<<dim3(VB_DIV_CEIL(h, 32), layers, 2), 32, 0, s>>>(E, F, B, w, h, k);
+    k_fb_posterior<<<pg, pb, 0, s>>>(E, F, B, w, h);
+    k_fb_cols<<<dim3(VB_DIV_CEIL(w, 128), layers, 2), 128, 0, s>>>(E, F, B, w, h, k);
+    k_fb_posterior<<<pg, pb, 0, s>>>(E, F, B, w, h);
+}
+
+template <int DIR>
+void launch_global(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC, int step, cudaStream_t s) {
+    const bool rowdir = (DIR == DIR_L2R || DIR == DIR_R2L);
+    const int len = rowdir ? A.w : A.h, other = rowdir ? A.h : A.w;
+    if (step == 1) {
+        // a chain: identical to local propagation with one segment spanning the whole axis
+        k_local_propagation<DIR><<<dim3(VB_DIV_CEIL(other, 128), 1), dim3(128, 1), 0, s>>>(A, C, PC, len);
+        return;
+    }
+    const int n = (len - 2) / step + 1;  // number of evaluated positions along the axis (len >= 2)
+    if (len < 2) return;
+    if (rowdir)
+        k_global_propagation<DIR><<<dim3(VB_DIV_CEIL(n, 8), VB_DIV_CEIL(other, 16)), dim3(8, 16), 0, s>>>(A, C, PC, step);
+    else
+        k_global_propagation<DIR><<<dim3(VB_DIV_CEIL(n, 4), VB_DIV_CEIL(other, 32)), dim3(4, 32), 0, s>>>(A, C, PC, step);
+}
+
+template <int DIR>
+void launch_local(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC, int width, cudaStream_t s) {
+    const bool rowdir = (DIR == DIR_L2R || DIR == DIR_R2L);
+    const int len = rowdir ? A.w : A.h, other = rowdir ? A.h : A.w;
+    const int nseg = VB_DIV_CEIL(len, width);
+    k_local_propagation<DIR><<<dim3(VB_DIV_CEIL(other, 32), VB_DIV_CEIL(nseg, 4)), dim3(32, 4), 0, s>>>(A, C, PC, width);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int DepthEM::init_stream() {
+    if (!stream) VB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    return 0;
+}
+
+int DepthEM::seed_rng() {
+    const dim3 b(32, 8), g(VB_DIV_CEIL(w, 32), VB_DIV_CEIL(h, 8));
+    k_seed_rng<<<g, b, 0, stream>>>(rng.ptr, w, h, rng.pitch, rng.layer_elems());
+    VB_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+int DepthEM::ensure(int w_, int h_, int N, int N_dp) {
+    if (init_stream()) return (int)cudaErrorUnknown;
+    w = w_, h = h_;
+    if (rng.ensure(w, h, 6, false)) {
+        if (int e = seed_rng()) return e;
+    }
+    cost.ensure(w, h, 1, false);
+    depth.ensure(w, h, 1, false);
+    if (N > 0) {
+        if (!shared_flows) flows.ensure(w, h, N, true);
+        rig.ensure(w, h, N, true);
+    }
+    if (N_dp > 0) {
+        dp.ensure(w, h, N_dp, true);
+        dp_pconf.ensure(w, h, N_dp, true);
+        dp_conf.ensure(w, h, N_dp, true);
+    }
+    const int L = N > N_dp ? N : N_dp;
+    if (L > 0) {
+        fb_fwd.ensure(w, h, L, true);
+        fb_bwd.ensure(w, h, L, true);
+    }
+    VB_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+int DepthEM::run(int N, int N_dp, const DepthHyper& hp, bool update_rigidness_only) {
+    DepthView A;
+    A.N = N, A.N_dp = N_dp, A.w = w, A.h = h;
+    A.pitch = depth.pitch, A.plane = depth.layer_elems();
+    A.abs_rf = hp.abs_resize_factor, A.basefocal = hp.basefocal, A.lambda = hp.lambda, A.omega = hp.omega;
+    A.delta = hp.delta, A.disp_delta = hp.disp_delta, A.range_factor = hp.range_factor;
+    const TexStack<float2>& fl = shared_flows ? *shared_flows : flows;
+    A.flows_tex = fl.tex;
+    A.dp_tex = dp.tex, A.dp_pconf_tex = dp_pconf.tex, A.dp_conf_tex = dp_conf.tex;
+    A.rig = rig.ptr, A.depth = depth.ptr, A.cost = cost.ptr, A.rng = rng.ptr;
+    A.dp_conf = dp_conf.ptr;
+    A.dp_conf_pitch = (int)(dp_conf.pitch / sizeof(float));
+    A.dp_conf_plane = (size_t)A.dp_conf_pitch * h;
+
+    cudaStream_t s = stream;
+    const dim3 pb(32, 8), pg(VB_DIV_CEIL(w, 32), VB_DIV_CEIL(h, 8));
+
+    if (!update_rigidness_only) {
+        if (hp.fb_smooth) {
+            if (N > 0) {
+                StackView E{rig.ptr, rig.pitch, rig.layer_elems()};
+                StackView F{fb_fwd.ptr, fb_fwd.pitch, fb_fwd.layer_elems()};
+                StackView B{fb_bwd.ptr, fb_bwd.pitch, fb_bwd.layer_elems()};
+                fb_smooth_stack(E, F, B, N, w, h, hp.s0_ems_prob, hp.no_change_prob, s);
+            }
+            if (N_dp > 0) {
+                StackView E{dp_conf.ptr, A.dp_conf_pitch, A.dp_conf_plane};
+                StackView F{fb_fwd.ptr, fb_fwd.pitch, fb_fwd.layer_elems()};
+                StackView B{fb_bwd.ptr, fb_bwd.pitch, fb_bwd.layer_elems()};
+                fb_smooth_stack(E, F, B, N_dp, w, h, hp.s0_ems_prob, hp.no_change_prob, s);
+            }
+            VB_RETURN_IF_CUDA_ERROR();
+        }
+        k_cost_and_random_search<<<pg, pb, 0, s>>>(A, cam, pcam, hp.n_rand_samples);
+        VB_RETURN_IF_CUDA_ERROR();
+        if (hp.global_prop_step > 0) {
+            launch_global<DIR_L2R>(A, cam, pcam, hp.global_prop_step, s);
+            launch_global<DIR_B2T>(A, cam, pcam, hp.global_prop_step, s);
+            launch_global<DIR_R2L>(A, cam, pcam, hp.global_prop_step, s);
+            launch_global<DIR_T2B>(A, cam, pcam, hp.global_prop_step, s);
+        }
+        if (hp.local_prop_width > 0) {
+            launch_local<DIR_L2R>(A, cam, pcam, hp.local_prop_width, s);
+            launch_local<DIR_B2T>(A, cam, pcam, hp.local_prop_width, s);
+            launch_local<DIR_R2L>(A, cam, pcam, hp.local_prop_width, s);
+            launch_local<DIR_T2B>(A, cam, pcam, hp.local_prop_width, s);
+        }
+        VB_RETURN_IF_CUDA_ERROR();
+    }
+    k_update_rigidness<<<pg, pb, 0, s>>>(A, cam, pcam);
+    VB_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+DepthEM& global_depth_em() {
+    static DepthEM inst;
+    return inst;
+}
+
+}  // namespace vb

@@ -1,0 +1,59 @@
+// Depth / rigidness EM state and driver (device-resident).
+//
+// Replaces the reference's optimize_depth.cu file-static GMats + 26-launch host driver
+// (reference: gpu-kernels/optimize_depth.cu:24-52 state, :293-520 driver, fb_smooth.h:17-109).
+// One DepthEM instance per process/device keeps what the reference keeps in file statics, including the
+// per-pixel XORWOW streams that advance across calls and windows (optimize_depth.cu:357-361).
+#pragma once
+#include "common.cuh"
+
+namespace vb {
+
+struct DepthHyper {
+    float abs_resize_factor, basefocal;
+    int n_rand_samples, global_prop_step, local_prop_width;
+    float lambda, omega, disp_delta, delta;
+    bool fb_smooth;
+    float s0_ems_prob, no_change_prob;
+    float range_factor;
+};
+
+struct DepthEM {
+    // geometry of the cached window
+    int w = 0, h = 0;
+    // device state
+    TexStack<float2> flows;      // N layers, bilinear fetched
+    Plane<float> rig;            // N layers, rigidness maps W_f
+    Plane<float> depth, cost;    // 1 layer each
+    Plane<uint32_t> rng;         // 6 layers: XORWOW d, v0..v4 (SoA)
+    TexStack<float> dp, dp_pconf, dp_conf;  // N_dp layers each, bilinear fetched
+    Plane<float> fb_fwd, fb_bwd;            // message scratch, max(N, N_dp) layers
+    CamBlock cam;
+    PriorCamBlock pcam;
+    cudaStream_t stream = nullptr;
+    // when set, kernels fetch flows from this stack instead of `flows` (window pipeline shares one upload)
+    TexStack<float2>* shared_flows = nullptr;
+
+    int init_stream();
+    // (Re)allocate for a window geometry; mirrors the reference's lazy create() calls
+    // (optimize_depth.cu:357-375,391-404,427-458).  Re-seeds the RNG plane iff (w,h) changed.
+    int ensure(int w_, int h_, int N, int N_dp);
+    int seed_rng();
+
+    void set_K(const float* h_K) { fill_K(cam, h_K); }
+    void set_pose(int f, const float* R9, const float* t3) {
+        memcpy(cam.R[f], R9, 9 * sizeof(float));
+        memcpy(cam.t[f], t3, 3 * sizeof(float));
+    }
+    void set_prior_pose(int f, const float* R9, const float* t3) {
+        memcpy(pcam.R[f], R9, 9 * sizeof(float));
+        memcpy(pcam.t[f], t3, 3 * sizeof(float));
+    }
+
+    // One M-step (unless rigidness_only) + E-step on the device-resident state.  Asynchronous on `stream`.
+    int run(int N, int N_dp, const DepthHyper& hp, bool update_rigidness_only);
+};
+
+DepthEM& global_depth_em();
+
+}  // namespace vb

@@ -1,0 +1,50 @@
+// Mode seeking over the pose-hypothesis pool: Gaussian mean-shift and truncated robust Gaussian fit.
+//
+// Replaces reference gpu-kernels/meanshift.cu:34-150 (host loop of <=100 iterations, each 1 kernel +
+// 2 multi-pass reductions + 2 blocking D2H + 1 cudaMemcpyToSymbol) with ONE persistent single-CTA kernel
+// that runs all iterations on the device, and reference gpu-kernels/fit_robust_gaussian.cu:101-286 with one
+// fused E-step+reduction launch per iteration (the 6x6 FP64 determinant/inverse/shrinkage stays on the
+// host, as in the reference: aux_funs.cpp:101-141).
+#pragma once
+#include "common.cuh"
+
+namespace vb {
+
+constexpr int kMeanshiftMaxDims = 16;  // reference: meanshift.cu:5
+constexpr int kRobustMaxDims = 6;      // reference: fit_robust_gaussian.cu:6
+
+struct MeanshiftResult {
+    float mean[kMeanshiftMaxDims];
+    float confidence;
+    float weight_sum;  // last sum of kernel weights (trial mode: the trial's weight sum)
+    int used_iters;
+    int n;             // pool size seen by the kernel
+};
+
+struct PoseMode {
+    cudaStream_t stream = nullptr;
+    MeanshiftResult* d_result = nullptr;  // device
+    MeanshiftResult* h_result = nullptr;  // pinned host mirror
+    float* d_partials = nullptr;
+    // robust fit scratch
+    float* d_rg_scratch = nullptr;
+    size_t rg_capacity = 0;
+    float* d_rg_sums = nullptr;
+    float* h_rg_sums = nullptr;  // pinned
+
+    int init();
+    // Mean-shift on d_space[N][dims]; N is read from d_n when non-null.  Blocks until the result is on the host
+    // (needed by the caller's control flow).  Semantics of every argument as in the reference ABI.
+    int meanshift(const float* d_space, const float* h_space_for_init, const int* d_n, int n_host, int dims,
+                  float kernel_var, float* h_io_mean, float* h_o_confidence, int* used_iters,
+                  bool use_external_init_mean, float epsilon, int max_iters, int max_init_trials,
+                  float good_init_confidence);
+    // Robust Gaussian fit on x = scale * d_space (scale folds the caller's pose scaling).
+    int fit_robust_gaussian(const float* d_space, int N, int dims, float scale, float* h_io_mean,
+                            float* h_io_covar, float trunc_sigma, float covar_reg_lambda, float* h_o_density,
+                            int* used_iters, float epsilon, int max_iters);
+};
+
+PoseMode& global_pose_mode();
+
+}  // namespace vb
