@@ -1,0 +1,620 @@
+// TEST INFRASTRUCTURE (oracle). Not part of the shipped product.
+//
+// CPU port of the EM hot path behind the same library-level ABI (symbols prefixed cpu_), plain C++ with
+// OpenMP over pixels / hypotheses.  It restates the reference's CUDA kernels line by line in scalar FP32:
+//   residual model            gpu-kernels/residual_model.h:6-68
+//   stacked bilinear fetch    gpu-kernels/gmat.h:39-66,175-179 (CUDA linear filtering emulated: 8-bit weights,
+//                             layers stacked in y, clamp at the stack border)
+//   depth step                gpu-kernels/optimize_depth.cu:84-291 (kernels), :462-494 (schedule)
+//   forward-backward smoother gpu-kernels/fb_smooth.h:29-107
+//   per-pixel XORWOW          cuRAND's own curand_init/curand_uniform compiled for the host
+//                             (curand_kernel.h:60-62 QUALIFIERS override) -> identical streams
+//   P3P instance collector    gpu-kernels/collect_p3p_instances.cu:57-145
+//   batched P3P               gpu-kernels/solve_batch_lambdatwist.cu:11-42 with the reference's own
+//                             lambdatwist/*.h compiled for the host when /root/reference is available at build
+//                             time (HAVE_REF_LAMBDATWIST), R->rvec by ../voldor_b200/csrc/host_math.h (the
+//                             reference's CPU branch uses cv::Rodrigues there, voldor/geometry.cpp:118)
+//   mean-shift                gpu-kernels/meanshift.cu:12-150 + reduce_vector_sum.h:12-57 (same tree order)
+//   robust Gaussian fit       gpu-kernels/fit_robust_gaussian.cu:56-286 + aux_funs.cpp:101-141
+// Purpose: (1) GPU-less logic tests, (2) the `cpu_baseline` / `--impl reference` leg of bench.py (the reference
+// has no CPU implementation of the E/M steps: voldor.cpp:254,274 call CUDA), (3) tolerance-level
+// cross-check of the GPU results.  Bit-level truth for parity is oracle/_ref (the reference kernels
+// themselves on the GPU); libm's powf/expf/logf differ from libdevice in the last bits, so this port is
+// compared with tolerances and "fraction of pixels within tolerance".
+// PARITY PINNING: the reference ships no tests or golden vectors; this port is pinned against
+// outputs of the reference kernels generated on the GPU box (tests/golden/*.npz, tests/make_golden.py).
+#define QUALIFIERS static inline
+#include <cuda_runtime.h>
+#include <curand_kernel.h>
+
+#include "../voldor_b200/csrc/host_math.h"
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#ifdef HAVE_REF_LAMBDATWIST
+#include "lambdatwist/lambdatwist_p4p.h"
+#endif
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// residual model (residual_model.h)
+// ---------------------------------------------------------------------------------------------------
+inline float fmag_c(float fmag) {
+    fmag = std::fmin(std::fmax(fmag * 0.5f, 2.f), 100.f);
+    return 1.0f + -0.0022f * fmag;
+}
+inline float fmag_scale(float fmag) {
+    fmag = std::fmin(std::fmax(fmag * 0.5f, 2.f), 100.f);
+    return 0.01f * std::exp(0.09f * fmag);
+}
+inline float fisk_pdf(float x, float c, float scale) {
+    x = std::fmax(x * 0.5f, FLT_EPSILON);
+    const float q = (x * x) / scale;
+    return (c * std::pow(q, -c - 1.f) * std::pow(1 + std::pow(q, -c), -2.f)) / scale;
+}
+inline float l2n(float x, float y) { return std::sqrt(x * x + y * y); }
+inline float fun_rigidness(float dx1, float dy1, float dx2, float dy2, float lambda, float abs_rf) {
+    const float obs = l2n(dx2, dy2) / abs_rf;
+    const float diff = l2n(dx1 - dx2, dy1 - dy2) / abs_rf;
+    const float c = fmag_c(obs), s = fmag_scale(obs);
+    const float p = fisk_pdf(diff, c, s), mu = fisk_pdf(lambda * obs, c, s);
+    return p / (p + mu);
+}
+inline float fun_depth_rigidness(float d1, float d2, float basefocal, float omega, float abs_rf) {
+    const float disp1 = (basefocal / d1) / abs_rf, disp2 = (basefocal / d2) / abs_rf;
+    const float diff = std::fabs(disp1 - disp2);
+    const float c = fmag_c(disp2), s = fmag_scale(disp2);
+    const float p = fisk_pdf(diff, c, s), mu = fisk_pdf(omega * disp2, c, s);
+    return p / (p + mu);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stacked layered image with emulated CUDA bilinear filtering (gmat.h)
+// ---------------------------------------------------------------------------------------------------
+template <int CH>
+struct Stack {
+    std::vector<float> data;
+    int w = 0, h = 0, layers = 0;
+    bool ensure(int w_, int h_, int l_) {  // lazy layers: keep a larger allocation (gmat.h:19-22)
+        if (w_ == w && h_ == h && l_ <= layers) return false;
+        w = w_, h = h_, layers = l_;
+        data.assign((size_t)w * h * layers * CH, 0.f);
+        return true;
+    }
+    float* layer(int d) { return data.data() + (size_t)d * w * h * CH; }
+    inline void tex(float x, float y, int d, float* out) const {
+        // tex2D(x + 0.5, d*h + y + 0.5), linear filter, clamp, unnormalised
+        const float xb = (x + 0.5f) - 0.5f, yb = ((float)((size_t)d * h) + y + 0.5f) - 0.5f;
+        const float fx = std::floor(xb), fy = std::floor(yb);
+        const float a = std::floor((xb - fx) * 256.f + 0.5f) * (1.f / 256.f);
+        const float b = std::floor((yb - fy) * 256.f + 0.5f) * (1.f / 256.f);
+        const int H = h * layers;
+        const int x0 = std::min(std::max((int)fx, 0), w - 1), x1 = std::min(std::max((int)fx + 1, 0), w - 1);
+        const int y0 = std::min(std::max((int)fy, 0), H - 1), y1 = std::min(std::max((int)fy + 1, 0), H - 1);
+        for (int c = 0; c < CH; c++) {
+            const float t00 = data[((size_t)y0 * w + x0) * CH + c], t10 = data[((size_t)y0 * w + x1) * CH + c];
+            const float t01 = data[((size_t)y1 * w + x0) * CH + c], t11 = data[((size_t)y1 * w + x1) * CH + c];
+            out[c] = (1 - a) * (1 - b) * t00 + a * (1 - b) * t10 + (1 - a) * b * t01 + a * b * t11;
+        }
+    }
+};
+
+struct Cam {
+    float K4[4], K4inv[4];
+    float R[16][9], t[16][3];
+};
+inline void set_K(Cam& c, const float* K) {
+    c.K4[0] = K[0], c.K4[1] = K[2], c.K4[2] = K[4], c.K4[3] = K[5];
+    c.K4inv[0] = 1.f / K[0], c.K4inv[1] = -K[2] / K[0], c.K4inv[2] = 1.f / K[4], c.K4inv[3] = -K[5] / K[4];
+}
+inline void p2_to_p3(const Cam& C, float px, float py, float depth, float& ox, float& oy, float& oz) {
+    ox = (C.K4inv[0] * px + C.K4inv[1]) * depth, oy = (C.K4inv[2] * py + C.K4inv[3]) * depth, oz = depth;
+}
+inline void p3_to_p2(const Cam& C, float ox, float oy, float oz, float& px, float& py) {
+    px = (C.K4[0] * ox + C.K4[1] * oz) / oz, py = (C.K4[2] * oy + C.K4[3] * oz) / oz;
+}
+inline void trans(const float* R, const float* t, float& ox, float& oy, float& oz) {
+    const float a = ox * R[0] + oy * R[1] + oz * R[2], b = ox * R[3] + oy * R[4] + oz * R[5],
+                c = ox * R[6] + oy * R[7] + oz * R[8];
+    ox = a + t[0], oy = b + t[1], oz = c + t[2];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// depth step state (optimize_depth.cu:45-52)
+// ---------------------------------------------------------------------------------------------------
+struct DepthState {
+    int w = 0, h = 0;
+    std::vector<curandStateXORWOW_t> rng;
+    Stack<2> flows;
+    Stack<1> rig, dp, dp_pconf, dp_conf;
+    std::vector<float> depth, cost;
+    Cam cam, pcam;
+    int N = 0, N_dp = 0;
+    float abs_rf, basefocal, lambda, omega, delta, disp_delta, range_factor;
+
+    float pixel_cost(int px, int py, float d) const {  // optimize_depth.cu:140-198
+        float cost_sum = 0, wsum = 0, ox, oy, oz, px1 = (float)px, py1 = (float)py, px2, py2;
+        p2_to_p3(cam, (float)px, (float)py, d, ox, oy, oz);
+        for (int f = 0; f < N; f++) {
+            trans(cam.R[f], cam.t[f], ox, oy, oz);
+            p3_to_p2(cam, ox, oy, oz, px2, py2);
+            if (oz > 0 && px1 >= 0 && px1 < w && py1 >= 0 && py1 < h) {
+                float d2[2];
+                flows.tex(px1, py1, f, d2);
+                const float dx1 = px2 - px1, dy1 = py2 - py1;
+                px1 = px2, py1 = py2;
+                const float wgt = rig.data[((size_t)f * h + py) * w + px];
+                cost_sum -= wgt * std::log(fun_rigidness(dx1, dy1, d2[0], d2[1], lambda, abs_rf));
+                wsum += wgt;
+            }
+        }
+        for (int f = 0; f < N_dp; f++) {
+            p2_to_p3(cam, (float)px, (float)py, d, ox, oy, oz);
+            trans(pcam.R[f], pcam.t[f], ox, oy, oz);
+            p3_to_p2(cam, ox, oy, oz, px1, py1);
+            if (oz > 0 && px1 >= 0 && px1 < w && py1 >= 0 && py1 < h) {
+                float td, tp, tc;
+                dp.tex(px1, py1, f, &td), dp_pconf.tex(px1, py1, f, &tp), dp_conf.tex(px1, py1, f, &tc);
+                if (td > 0) {
+                    const float wgt = tp * tc * ((disp_delta > 0 && f == 0) ? disp_delta : delta);
+                    cost_sum -= wgt * std::log(fun_depth_rigidness(oz, td, basefocal, omega, abs_rf));
+                    wsum += wgt;
+                }
+            }
+        }
+        if (wsum == 0) return INFINITY;
+        return cost_sum / std::fmax(wsum, FLT_EPSILON);
+    }
+    inline void try_depth(int x, int y, float cand) {
+        const float c = pixel_cost(x, y, cand);
+        float& cc = cost[(size_t)y * w + x];
+        if (c < cc) depth[(size_t)y * w + x] = cand, cc = c;
+    }
+    void update_rigidness() {  // optimize_depth.cu:84-138
+#pragma omp parallel for schedule(dynamic, 4)
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                const float d = depth[(size_t)y * w + x];
+                float ox, oy, oz, px1 = (float)x, py1 = (float)y, px2, py2;
+                p2_to_p3(cam, (float)x, (float)y, d, ox, oy, oz);
+                for (int f = 0; f < N; f++) {
+                    trans(cam.R[f], cam.t[f], ox, oy, oz);
+                    p3_to_p2(cam, ox, oy, oz, px2, py2);
+                    float r = 0;
+                    if (oz > 0 && px1 >= 0 && px1 < w && py1 >= 0 && py1 < h) {
+                        float d2[2];
+                        flows.tex(px1, py1, f, d2);
+                        const float dx1 = px2 - px1, dy1 = py2 - py1;
+                        px1 = px2, py1 = py2;
+                        r = fun_rigidness(dx1, dy1, d2[0], d2[1], lambda, abs_rf);
+                    }
+                    rig.data[((size_t)f * h + y) * w + x] = r;
+                }
+                for (int f = 0; f < N_dp; f++) {
+                    p2_to_p3(cam, (float)x, (float)y, d, ox, oy, oz);
+                    trans(pcam.R[f], pcam.t[f], ox, oy, oz);
+                    p3_to_p2(cam, ox, oy, oz, px1, py1);
+                    float& conf = dp_conf.data[((size_t)f * h + y) * w + x];
+                    if (oz > 0 && px1 >= 0 && px1 < w && py1 >= 0 && py1 < h) {
+                        float td;
+                        dp.tex(px1, py1, f, &td);
+                        if (td > 0) conf = fun_depth_rigidness(oz, td, basefocal, omega, abs_rf);
+                    } else
+                        conf = 0;
+                }
+            }
+    }
+};
+
+// fb_smooth.h:29-107 on a stack of `layers` maps
+void fb_smooth(float* maps, int layers, int w, int h, float s0e, float nc) {
+    const size_t plane = (size_t)w * h;
+    std::vector<float> F(plane * layers), B(plane * layers);
+    auto fwd = [&](float p, float e) {
+        const float s0 = (p * (1.f - nc) + (1.f - p) * nc) * s0e, s1 = (p * nc + (1.f - p) * (1 - nc)) * e;
+        return s1 / (s0 + s1);
+    };
+    auto bwd = [&](float p, float e) {
+        const float s0 = p * e * (1.f - nc) + (1.f - p) * nc * s0e, s1 = p * e * nc + (1.f - p) * (1.f - nc) * s0e;
+        return s1 / (s0 + s1);
+    };
+    auto post = [&]() {
+#pragma omp parallel for
+        for (long long i = 0; i < (long long)(plane * layers); i++) {
+            const float s0 = (1.f - F[i]) * (1.f - B[i]), s1 = F[i] * B[i];
+            maps[i] = s1 / (s0 + s1);
+        }
+    };
+#pragma omp parallel for collapse(2)
+    for (int d = 0; d < layers; d++)
+        for (int y = 0; y < h; y++) {
+            float* e = maps + d * plane + (size_t)y * w;
+            float p = e[0];
+            for (int i = 0; i < w; i++) F[d * plane + (size_t)y * w + i] = p = fwd(p, e[i]);
+            p = e[w - 1];
+            for (int i = w - 1; i >= 0; i--) B[d * plane + (size_t)y * w + i] = p = bwd(p, e[i]);
+        }
+    post();
+#pragma omp parallel for collapse(2)
+    for (int d = 0; d < layers; d++)
+        for (int x = 0; x < w; x++) {
+            float* e = maps + d * plane + x;
+            float p = e[0];
+            for (int i = 0; i < h; i++) F[d * plane + (size_t)i * w + x] = p = fwd(p, e[(size_t)i * w]);
+            p = e[(size_t)(h - 1) * w];
+            for (int i = h - 1; i >= 0; i--) B[d * plane + (size_t)i * w + x] = p = bwd(p, e[(size_t)i * w]);
+        }
+    post();
+}
+
+DepthState g_depth;
+
+// ---------------------------------------------------------------------------------------------------
+// reduce_vector_sum.h tree: 512-element blocks, pairs (i, i+256), strides 128..1, recursive over block results
+// ---------------------------------------------------------------------------------------------------
+float tree_sum(std::vector<float> v) {
+    while (v.size() > 1) {
+        const size_t n = v.size(), nb = (n + 511) / 512;
+        std::vector<float> out(nb);
+        for (size_t b = 0; b < nb; b++) {
+            float s[256];
+            for (int t = 0; t < 256; t++) {
+                const size_t idx = b * 512 + t;
+                s[t] = 0;
+                if (idx < n) {
+                    s[t] = v[idx];
+                    if (idx + 256 < n) s[t] += v[idx + 256];
+                }
+            }
+            for (int stride = 128; stride >= 1; stride >>= 1)
+                for (int t = 0; t < stride; t++) s[t] += s[t + stride];
+            out[b] = s[0];
+        }
+        v.swap(out);
+    }
+    return v.empty() ? 0.f : v[0];
+}
+
+}  // namespace
+
+extern "C" {
+
+// optimize_depth.cu:293-520
+int cpu_optimize_depth_gpu(float** h_flows, float** h_rig, float** h_o_rig, float** h_dp, float** h_pc, float** h_cf,
+                           float** h_o_cf, float* h_depth, float* h_o_depth, float* h_K, float** h_Rs, float** h_ts,
+                           float** h_dp_Rs, float** h_dp_ts, float abs_rf, int N, int N_dp, int w, int h,
+                           float basefocal, int n_rand, int gstep, int lwidth, float lambda, float omega,
+                           float disp_delta, float delta, int fb, float s0e, float nc, float range_factor,
+                           int rig_only) {
+    DepthState& S = g_depth;
+    const size_t npx = (size_t)w * h;
+    S.N = N, S.N_dp = N_dp;
+    S.abs_rf = abs_rf, S.basefocal = basefocal, S.lambda = lambda, S.omega = omega, S.delta = delta;
+    S.disp_delta = disp_delta, S.range_factor = range_factor;
+    if (h_K) set_K(S.cam, h_K);
+    if (S.w != w || S.h != h) {
+        S.w = w, S.h = h;
+        S.rng.resize(npx);
+#pragma omp parallel for
+        for (long long i = 0; i < (long long)npx; i++) curand_init(233ULL, (unsigned long long)i, 0ULL, &S.rng[i]);
+        S.cost.assign(npx, 0), S.depth.assign(npx, 0);
+        S.flows = Stack<2>(), S.rig = Stack<1>(), S.dp = Stack<1>(), S.dp_pconf = Stack<1>(), S.dp_conf = Stack<1>();
+    }
+    if (h_depth) memcpy(S.depth.data(), h_depth, npx * sizeof(float));
+    if (N > 0) {
+        if (h_Rs)
+            for (int f = 0; f < N; f++) memcpy(S.cam.R[f], h_Rs[f], 36);
+        if (h_ts)
+            for (int f = 0; f < N; f++) memcpy(S.cam.t[f], h_ts[f], 12);
+        S.flows.ensure(w, h, N), S.rig.ensure(w, h, N);
+        if (h_flows)
+            for (int f = 0; f < N; f++) memcpy(S.flows.layer(f), h_flows[f], npx * 2 * sizeof(float));
+        if (h_rig)
+            for (int f = 0; f < N; f++) memcpy(S.rig.layer(f), h_rig[f], npx * sizeof(float));
+    }
+    if (N_dp > 0) {
+        if (h_dp_Rs)
+            for (int f = 0; f < N_dp; f++) memcpy(S.pcam.R[f], h_dp_Rs[f], 36);
+        if (h_dp_ts)
+            for (int f = 0; f < N_dp; f++) memcpy(S.pcam.t[f], h_dp_ts[f], 12);
+        S.dp.ensure(w, h, N_dp), S.dp_pconf.ensure(w, h, N_dp), S.dp_conf.ensure(w, h, N_dp);
+        if (h_dp)
+            for (int f = 0; f < N_dp; f++) memcpy(S.dp.layer(f), h_dp[f], npx * sizeof(float));
+        if (h_pc)
+            for (int f = 0; f < N_dp; f++) memcpy(S.dp_pconf.layer(f), h_pc[f], npx * sizeof(float));
+        if (h_cf)
+            for (int f = 0; f < N_dp; f++) memcpy(S.dp_conf.layer(f), h_cf[f], npx * sizeof(float));
+    }
+    if (!rig_only) {
+        if (fb) {
+            if (N > 0) fb_smooth(S.rig.data.data(), N, w, h, s0e, nc);
+            if (N_dp > 0) fb_smooth(S.dp_conf.data.data(), N_dp, w, h, s0e, nc);
+        }
+        // cost map + random samples (optimize_depth.cu:269-284,472-478)
+#pragma omp parallel for schedule(dynamic, 4)
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                const size_t i = (size_t)y * w + x;
+                S.cost[i] = S.pixel_cost(x, y, S.depth[i]);
+                for (int it = 0; it < n_rand; it++) {
+                    const float d = 1.0f / (range_factor * curand_uniform(&S.rng[i]) + (1.0f / 1e5f));
+                    S.try_depth(x, y, d);
+                }
+            }
+        if (gstep > 0) {  // global propagation L2R, B2T, R2L, T2B (optimize_depth.cu:209-235,480-485)
+#pragma omp parallel for
+            for (int y = 0; y < h; y++)
+                for (int x = 1; x < w; x += gstep) S.try_depth(x, y, S.depth[(size_t)y * w + x - 1]);
+#pragma omp parallel for
+            for (int x = 0; x < w; x++)
+                for (int y = h - 2; y >= 0; y -= gstep) S.try_depth(x, y, S.depth[(size_t)(y + 1) * w + x]);
+#pragma omp parallel for
+            for (int y = 0; y < h; y++)
+                for (int x = w - 2; x >= 0; x -= gstep) S.try_depth(x, y, S.depth[(size_t)y * w + x + 1]);
+#pragma omp parallel for
+            for (int x = 0; x < w; x++)
+                for (int y = 1; y < h; y += gstep) S.try_depth(x, y, S.depth[(size_t)(y - 1) * w + x]);
+        }
+        if (lwidth > 0) {  // local propagation, same order (optimize_depth.cu:237-267,486-491)
+            const int nsx = (w + lwidth - 1) / lwidth, nsy = (h + lwidth - 1) / lwidth;
+#pragma omp parallel for collapse(2)
+            for (int y = 0; y < h; y++)
+                for (int sx = 0; sx < nsx; sx++) {
+                    const int p0 = sx * lwidth;
+                    for (int x = std::max(1, p0 + 1); x < std::min(w, p0 + lwidth); x++)
+                        S.try_depth(x, y, S.depth[(size_t)y * w + x - 1]);
+                }
+#pragma omp parallel for collapse(2)
+            for (int x = 0; x < w; x++)
+                for (int sy = 0; sy < nsy; sy++) {
+                    const int p0 = sy * lwidth;
+                    for (int y = std::min(h - 2, p0 + lwidth - 2); y >= std::max(0, p0); y--)
+                        S.try_depth(x, y, S.depth[(size_t)(y + 1) * w + x]);
+                }
+#pragma omp parallel for collapse(2)
+            for (int y = 0; y < h; y++)
+                for (int sx = 0; sx < nsx; sx++) {
+                    const int p0 = sx * lwidth;
+                    for (int x = std::min(w - 2, p0 + lwidth - 2); x >= std::max(0, p0); x--)
+                        S.try_depth(x, y, S.depth[(size_t)y * w + x + 1]);
+                }
+#pragma omp parallel for collapse(2)
+            for (int x = 0; x < w; x++)
+                for (int sy = 0; sy < nsy; sy++) {
+                    const int p0 = sy * lwidth;
+                    for (int y = std::max(1, p0 + 1); y < std::min(h, p0 + lwidth); y++)
+                        S.try_depth(x, y, S.depth[(size_t)(y - 1) * w + x]);
+                }
+        }
+    }
+    S.update_rigidness();
+    if (h_o_depth) memcpy(h_o_depth, S.depth.data(), npx * sizeof(float));
+    if (h_o_rig)
+        for (int f = 0; f < N; f++) memcpy(h_o_rig[f], S.rig.layer(f), npx * sizeof(float));
+    if (h_o_cf)
+        for (int f = 0; f < N_dp; f++) memcpy(h_o_cf[f], S.dp_conf.layer(f), npx * sizeof(float));
+    return 0;
+}
+
+// collect_p3p_instances.cu:70-250
+int cpu_collect_p3p_instances(float** h_flows, float** h_rig, float* h_depth, float* h_K, float** h_Rs, float** h_ts,
+                              float* o_p2, float* o_p3, int N, int w, int h, int active_idx, float rig_thresh,
+                              float rig_sum_thresh, float min_d, float max_d, int max_trace) {
+    static Stack<2> flows;
+    static Stack<1> rig;
+    static std::vector<float> depth;
+    static Cam cam;
+    const size_t npx = (size_t)w * h;
+    if (h_K) set_K(cam, h_K);
+    if (h_Rs)
+        for (int f = 0; f < N; f++) memcpy(cam.R[f], h_Rs[f], 36);
+    if (h_ts)
+        for (int f = 0; f < N; f++) memcpy(cam.t[f], h_ts[f], 12);
+    flows.ensure(w, h, N), rig.ensure(w, h, N);
+    if (h_flows)
+        for (int f = 0; f < N; f++) memcpy(flows.layer(f), h_flows[f], npx * 2 * sizeof(float));
+    if (h_rig)
+        for (int f = 0; f < N; f++) memcpy(rig.layer(f), h_rig[f], npx * sizeof(float));
+    if (depth.size() != npx) depth.assign(npx, 0);
+    if (h_depth) memcpy(depth.data(), h_depth, npx * sizeof(float));
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const size_t i = (size_t)y * w + x;
+            float* p2 = o_p2 + i * 2;
+            float* p3 = o_p3 + i * 3;
+            p2[0] = p2[1] = p3[0] = p3[1] = p3[2] = NAN;
+            const float d = depth[i];
+            if (d < min_d || (max_d > 0 && d > max_d)) continue;
+            if (rig_sum_thresh > N + 1) {
+                float s = 0;
+                for (int f = 0; f < N; f++) s += rig.data[(size_t)f * npx + i];
+                if (s < rig_sum_thresh) continue;
+            }
+            int n_trace = 0;
+            float tp = 1;
+            for (int f = active_idx; f >= (max_trace > 0 ? std::max(0, active_idx - max_trace + 1) : 0); f--) {
+                tp *= rig.data[(size_t)f * npx + i];
+                if (tp > rig_thresh)
+                    n_trace++;
+                else
+                    break;
+            }
+            if (n_trace <= 0) continue;
+            bool out = false;
+            float px = 0, py = 0, ox, oy, oz;
+            p2_to_p3(cam, (float)x, (float)y, d, ox, oy, oz);
+            for (int f = 0; f <= active_idx; f++) {
+                if (f >= active_idx - n_trace + 1) {
+                    if (f == active_idx - n_trace + 1) p3_to_p2(cam, ox, oy, oz, px, py);
+                    if (px > 0 && px < w && py > 0 && py < h) {
+                        float d2[2];
+                        flows.tex(px, py, f, d2);
+                        px += d2[0], py += d2[1];
+                    } else {
+                        out = true;
+                        break;
+                    }
+                }
+                if (f < active_idx) trans(cam.R[f], cam.t[f], ox, oy, oz);
+            }
+            if (!out && oz > min_d && (max_d <= 0 || oz < max_d)) p2[0] = px, p2[1] = py, p3[0] = ox, p3[1] = oy, p3[2] = oz;
+        }
+    return 0;
+}
+
+// solve_batch_lambdatwist.cu:11-102 (indices from the same cuRAND streams)
+int cpu_solve_batch_p3p_lambdatwist_gpu(float* h_p3s, float* h_p2s, float* o_rvecs, float* o_tvecs, float* h_K,
+                                        int N_pts, int N_poses) {
+#ifdef HAVE_REF_LAMBDATWIST
+    const float fx = h_K[0], cx = h_K[2], fy = h_K[4], cy = h_K[5];
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int idx = 0; idx < N_poses; idx++) {
+        curandStateXORWOW_t st;
+        curand_init(233ULL, (unsigned long long)idx, 0ULL, &st);
+        int i[4];
+        for (int k = 0; k < 4; k++) i[k] = std::min((int)(curand_uniform(&st) * N_pts), N_pts - 1);
+        float R[3][3], t[3];
+        const bool ok = lambdatwist_p4p<float, float, 5>(&h_p2s[i[0] * 2], &h_p2s[i[1] * 2], &h_p2s[i[2] * 2],
+                                                         &h_p2s[i[3] * 2], &h_p3s[i[0] * 3], &h_p3s[i[1] * 3],
+                                                         &h_p3s[i[2] * 3], &h_p3s[i[3] * 3], fx, fy, cx, cy, R, t);
+        float* rv = o_rvecs + idx * 3;
+        float* tv = o_tvecs + idx * 3;
+        if (!ok) {
+            rv[0] = rv[1] = rv[2] = tv[0] = tv[1] = tv[2] = NAN;
+            continue;
+        }
+        tv[0] = t[0], tv[1] = t[1], tv[2] = t[2];
+        vb::hm::matrix_to_rvec(&R[0][0], rv);
+    }
+    return 0;
+#else
+    (void)h_p3s, (void)h_p2s, (void)o_rvecs, (void)o_tvecs, (void)h_K, (void)N_pts, (void)N_poses;
+    printf("oracle: built without the reference lambdatwist headers\n");
+    return 1;
+#endif
+}
+int cpu_solve_batch_p3p_ap3p_gpu(float* a, float* b, float* c, float* d, float* e, int n, int m) {
+    // the CPU port carries one minimal solver; AP3P parity is checked against oracle/_ref on the GPU
+    return cpu_solve_batch_p3p_lambdatwist_gpu(a, b, c, d, e, n, m);
+}
+
+// meanshift.cu:34-150
+int cpu_meanshift_gpu(float* space, float kernel_var, float* io_mean, float* o_conf, int* used_iters, int external,
+                      int N, int dims, float eps, int max_iters, int max_trials, float good_conf) {
+    std::vector<float> c_mean(io_mean, io_mean + dims), wv(N);
+    std::vector<std::vector<float>> ws(dims, std::vector<float>(N));
+    auto weights = [&](bool only_w) {
+#pragma omp parallel for
+        for (int i = 0; i < N; i++) {
+            float l2 = 0;
+            for (int d = 0; d < dims; d++) l2 += (space[i * dims + d] - c_mean[d]) * (space[i * dims + d] - c_mean[d]);
+            const float wgt = std::exp(-l2 / (2 * kernel_var));
+            wv[i] = wgt;
+            if (!only_w)
+                for (int d = 0; d < dims; d++) ws[d][i] = space[i * dims + d] * wgt;
+        }
+    };
+    if (!external) {
+        float best = 0;
+        int best_idx = -1;
+        for (int trial = 0; trial < max_trials; trial++) {
+            const int idx = rand() % N;
+            for (int d = 0; d < dims; d++) c_mean[d] = space[idx * dims + d];
+            weights(true);
+            const float s = tree_sum(wv);
+            if (s > best) best = s, best_idx = idx;
+            if (best > good_conf * N) break;
+        }
+        for (int d = 0; d < dims; d++) c_mean[d] = space[best_idx * dims + d];
+    }
+    if (used_iters) *used_iters = 0;
+    for (int iter = 0; iter < max_iters; iter++) {
+        weights(false);
+        const float wsum = tree_sum(wv);
+        std::vector<float> m(dims);
+        for (int d = 0; d < dims; d++) m[d] = tree_sum(ws[d]) / wsum;
+        if (o_conf) *o_conf = wsum / N;
+        if (used_iters) *used_iters = iter + 1;
+        float disp = 0;
+        for (int d = 0; d < dims; d++) disp += (io_mean[d] - m[d]) * (io_mean[d] - m[d]);
+        disp = std::sqrt(disp);
+        for (int d = 0; d < dims; d++) io_mean[d] = m[d];
+        if (disp < eps) break;
+        for (int d = 0; d < dims; d++) c_mean[d] = io_mean[d];
+    }
+    return 0;
+}
+
+double inverse(double* mat, double* mat_inv, int N);  // oracle/ref_shim/aux_shim.cpp (linked in)
+double regularize_covar_LW_given_lambda(double* mat, double* mat_ret, double lambda, int dims);
+
+// fit_robust_gaussian.cu:101-286 (dims must be 6: aux functions are 6x6, aux_funs.cpp:101-119)
+int cpu_fit_robust_gaussian(float* space, float* io_mean, float* io_covar, float trunc_sigma, float reg_lambda,
+                            float* o_density, int* used_iters, int N, int dims, float eps, int max_iters) {
+    if (dims != 6) return 1;
+    const int cd = 21;
+    float ht_weight = 0, mean[6], cov[21], cinv[21];
+    double full[36], inv[36];
+    for (int d = 0; d < 6; d++) mean[d] = io_mean[d];
+    for (int d1 = 0; d1 < 6; d1++)
+        for (int d2 = 0; d2 <= d1; d2++) cov[(d1 * d1 + d1) / 2 + d2] = io_covar[d1 * 6 + d2];
+    std::vector<float> W(N);
+    std::vector<std::vector<float>> WS(6, std::vector<float>(N)), WC(cd, std::vector<float>(N));
+    if (used_iters) *used_iters = 0;
+    int iter;
+    bool reliable = true;
+    for (iter = 0; iter < max_iters; iter++) {
+        for (int d1 = 0; d1 < 6; d1++)
+            for (int d2 = 0; d2 <= d1; d2++) full[d1 * 6 + d2] = full[d2 * 6 + d1] = (double)cov[(d1 * d1 + d1) / 2 + d2];
+        if (iter > 0 && reg_lambda > 0) regularize_covar_LW_given_lambda(full, full, reg_lambda, 6);
+        if (inverse(full, inv, 6) <= 0) {
+            reliable = false;
+            break;
+        }
+        for (int d1 = 0; d1 < 6; d1++)
+            for (int d2 = 0; d2 <= d1; d2++)
+                cov[(d1 * d1 + d1) / 2 + d2] = (float)full[d1 * 6 + d2], cinv[(d1 * d1 + d1) / 2 + d2] = (float)inv[d1 * 6 + d2];
+        const float prev = ht_weight / N;
+#pragma omp parallel for
+        for (int i = 0; i < N; i++) {
+            float diff[6], z = 0;
+            for (int d = 0; d < 6; d++) diff[d] = space[i * 6 + d] - mean[d];
+            for (int d1 = 0; d1 < 6; d1++) {
+                float tmp = 0;
+                for (int d2 = 0; d2 < 6; d2++)
+                    tmp += (d1 >= d2 ? cinv[(d1 * d1 + d1) / 2 + d2] : cinv[(d2 * d2 + d2) / 2 + d1]) * diff[d2];
+                z += tmp * diff[d1];
+            }
+            const float wgt = std::sqrt(z) < trunc_sigma ? 1.f : 0.f;
+            W[i] = wgt;
+            for (int d = 0; d < 6; d++) WS[d][i] = wgt * space[i * 6 + d];
+            for (int d1 = 0; d1 < 6; d1++)
+                for (int d2 = 0; d2 <= d1; d2++) WC[(d1 * d1 + d1) / 2 + d2][i] = wgt * diff[d1] * diff[d2];
+        }
+        ht_weight = tree_sum(W);
+        if (!std::isfinite(ht_weight)) {
+            reliable = false;
+            break;
+        }
+        if (std::fabs(ht_weight / N - prev) < eps) break;
+        for (int d = 0; d < 6; d++) mean[d] = tree_sum(WS[d]) / ht_weight;
+        for (int k = 0; k < cd; k++) cov[k] = tree_sum(WC[k]) / ht_weight;
+    }
+    if (reliable) {
+        if (o_density) *o_density = ht_weight / N;
+        if (used_iters) *used_iters = iter;
+        for (int d1 = 0; d1 < 6; d1++)
+            for (int d2 = 0; d2 <= d1; d2++) io_covar[d1 * 6 + d2] = io_covar[d2 * 6 + d1] = cov[(d1 * d1 + d1) / 2 + d2];
+        for (int d = 0; d < 6; d++) io_mean[d] = mean[d];
+    }
+    return reliable ? 0 : 1;
+}
+
+}  // extern "C"

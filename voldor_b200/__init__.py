@@ -1,0 +1,8 @@
+"""voldor_b200 — B200-native (sm_100a) implementation of VOLDOR's per-window EM inference hot path.
+
+The compute lives in voldor_b200/libvoldor_b200.so (hand-written CUDA, built in-tree by `make lib` or
+`__graft_entry__.build()`).  There is no CPU fallback: importing the bindings without the library, or
+calling them without a CUDA device, raises."""
+from .pyvoldor_vo import voldor, load_library, set_bootstrap_override, voldor_ex  # noqa: F401
+
+__all__ = ["voldor", "voldor_ex", "load_library", "set_bootstrap_override"]

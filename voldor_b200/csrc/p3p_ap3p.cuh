@@ -109,6 +109,13 @@ __device__ inline void m_mult(const float a[3][3], const float b[3][3], float r[
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) r[i][j] = a[i][0] * b[0][j] + a[i][1] * b[1][j] + a[i][2] * b[2][j];
 }
+// same product with the contraction the reference build uses for R = (Ck1nl*C13)*Cb1k3tzT: first term a rounded
+// multiply, the other two fused (verified in the reference's PTX; the compiler's choice is context dependent)
+__device__ inline void m_mult_first_plain(const float a[3][3], const float b[3][3], float r[3][3]) {
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+            r[i][j] = __fmaf_rn(a[i][2], b[2][j], __fmaf_rn(a[i][1], b[1][j], __fmul_rn(a[i][0], b[0][j])));
+}
 
 // b*: unit bearing vectors, w*: world points.  Up to 4 (R, t) with X_cam = R X_world + t.
 __device__ inline int compute_poses(const float b1[3], const float b2[3], const float b3[3], const float w1[3],
@@ -191,7 +198,7 @@ __device__ inline int compute_poses(const float b1[3], const float b2[3], const 
                                  {ctheta1p * stheta3, -stheta1p, ctheta1p * ctheta3}};
         float tm[3][3], R[3][3];
         m_mult(Ck1nl, C13, tm);
-        m_mult(tm, Cb1k3tzT, R);
+        m_mult_first_plain(tm, Cb1k3tzT, R);
 
         const float rp3[3] = {w3[0] * R[0][0] + w3[1] * R[1][0] + w3[2] * R[2][0],
                               w3[0] * R[0][1] + w3[1] * R[1][1] + w3[2] * R[2][1],

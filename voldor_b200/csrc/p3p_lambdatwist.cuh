@@ -84,7 +84,11 @@ __device__ inline Mat3 inverse3(const Mat3& a) {
     M(2, 0) = a(1, 0) * a(2, 1) - a(1, 1) * a(2, 0);
     M(2, 1) = a(0, 1) * a(2, 0) - a(0, 0) * a(2, 1);
     M(2, 2) = a(0, 0) * a(1, 1) - a(0, 1) * a(1, 0);
-    const float idet = 1.0f / (a(0, 0) * M(0, 0) + a(0, 1) * M(1, 0) + a(0, 2) * M(2, 0));
+    // a00*M00 + a01*M10 + a02*M20: the reference build keeps the FIRST product as a rounded multiply and fuses
+    // the other two (verified in its PTX); written out because the compiler's choice between the two legal
+    // contractions of x*y + z*w depends on surrounding code.
+    const float idet =
+        1.0f / __fmaf_rn(a(0, 2), M(2, 0), __fmaf_rn(a(0, 1), M(1, 0), __fmul_rn(a(0, 0), M(0, 0))));
     for (int i = 0; i < 9; ++i) M.m[i] *= idet;
     return M;
 }
@@ -150,11 +154,11 @@ __device__ inline void eig_known0(const Mat3& x, Mat3& E, Vec3& L) {
                     x(1, 1) * x(2, 2);
     float e1, e2;
     root2real(b, c, e1, e2);
-    if (fabsf(e1) < fabsf(e2)) {
-        const float t = e1;
-        e1 = e2;
-        e2 = t;
-    }
+    // NOTE (parity): solve_eig0.h:37-38 orders the pair with `if (|e1| < |e2|) std::swap(e1, e2)`.  std::swap is a
+    // host-only function there; in the reference's DEVICE build nvcc drops the call (and with it the whole
+    // conditional), so the GPU path never reorders the eigenvalues — verified in the PTX of the reference's
+    // solve kernel (no abs/compare between root2real and the eigenvector code).  The reference GPU build is
+    // the parity target (north_star), so the pair is deliberately left unordered here.
     L[0] = e1;
     L[1] = e2;
 
