@@ -83,6 +83,11 @@ int vb_py_voldor_wrapper_ex(const float* flows, const float* disparity, const fl
 /* Select the CUDA device used by this process' state (default: current device). */
 int vb_set_device(int device);
 
+/* In-library CUDA-event timing of the dominant kernel (fused cost + random depth search), for roofline
+ * reporting.  Enabling it adds one event synchronisation per launch, so it is off by default. */
+void vb_profile_enable(int on);
+void vb_profile_get(double* search_ms, long long* search_launches);
+
 /* Library self-description: returns a static string "voldor_b200 <version> sm_100a". */
 const char* vb_version(void);
 

@@ -283,6 +283,9 @@ float tree_sum(std::vector<float> v) {
 
 }  // namespace
 
+double inverse(double* mat, double* mat_inv, int N);  // oracle/ref_shim/aux_shim.cpp (linked in, C++ linkage)
+double regularize_covar_LW_given_lambda(double* mat, double* mat_ret, double lambda, int dims);
+
 extern "C" {
 
 // optimize_depth.cu:293-520
@@ -551,9 +554,6 @@ int cpu_meanshift_gpu(float* space, float kernel_var, float* io_mean, float* o_c
     }
     return 0;
 }
-
-double inverse(double* mat, double* mat_inv, int N);  // oracle/ref_shim/aux_shim.cpp (linked in)
-double regularize_covar_LW_given_lambda(double* mat, double* mat_ret, double lambda, int dims);
 
 // fit_robust_gaussian.cu:101-286 (dims must be 6: aux functions are 6x6, aux_funs.cpp:101-119)
 int cpu_fit_robust_gaussian(float* space, float* io_mean, float* io_covar, float trunc_sigma, float reg_lambda,

@@ -394,3 +394,21 @@ int oracle_py_voldor_wrapper(const float* flows_pt, const float* disparity_pt, c
 }
 
 }  // extern "C"
+
+// ---- small probes used by the GPU-less tests (host logic shared with the product: config grammar, rotations)
+extern "C" {
+
+void oracle_rvec_to_matrix(const float* rvec, float* R9) { vb::hm::rvec_to_matrix(rvec, R9); }
+void oracle_matrix_to_rvec(const float* R9, float* rvec) { vb::hm::matrix_to_rvec(R9, rvec); }
+
+// parse a flag string on top of the defaults; returns a few representative fields
+void oracle_config_probe(const char* cfg_str, float* out /*[12]*/) {
+    vb::Config c;
+    c.read(cfg_str);
+    out[0] = (float)c.max_iters, out[1] = c.no_trunc_iters, out[2] = (float)c.n_poses_to_sample;
+    out[3] = c.silent ? 1.f : 0.f, out[4] = c.lambda, out[5] = (float)c.lambdatwist, out[6] = c.meanshift_epsilon;
+    out[7] = (float)c.depth_rand_samples, out[8] = c.abs_resize_factor, out[9] = (float)c.exclusive_gpu_context;
+    out[10] = c.rg_pose_scaling, out[11] = (float)c.fb_smooth;
+}
+
+}  // extern "C"

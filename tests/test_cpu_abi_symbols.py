@@ -1,0 +1,61 @@
+"""The C-ABI shared library loads without a GPU and exports every symbol the headers in include/ declare
+(no compute calls here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import ffi
+
+INC = os.path.join(ffi.ROOT, "include")
+
+
+def _declared_c_symbols():
+    txt = open(os.path.join(INC, "voldor_b200.h")).read()
+    return sorted(set(re.findall(r"\b(vb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def _declared_cpp_symbols():
+    txt = open(os.path.join(INC, "gpu_kernels.h")).read() + open(os.path.join(INC, "py_export.h")).read()
+    return sorted(set(re.findall(r"(?:DLL_EXPORT|VB_EXPORT) int ([a-z0-9_]+)\s*\(", txt)))
+
+
+@pytest.mark.skipif(not os.path.exists(ffi.OURS), reason="libvoldor_b200.so not built (make lib)")
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(ffi.OURS)
+    names = _declared_c_symbols()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/voldor_b200.h but not exported"
+    # C++-linkage entry points keep the reference's mangled names (drop-in for voldor/*.cpp, pyvoldor_vo.pyx)
+    out = subprocess.check_output(["nm", "-D", "--defined-only", ffi.OURS], text=True)
+    for n in _declared_cpp_symbols():
+        assert re.search(rf"\b_Z\d+{n}", out), f"C++ symbol {n} missing"
+    lib.vb_version.restype = C.c_char_p
+    assert b"sm_100a" in lib.vb_version()
+
+
+@pytest.mark.skipif(not os.path.exists(ffi.REF), reason="oracle/_ref not built")
+def test_mangled_names_match_the_reference_build():
+    """the reference's own objects and ours export byte-identical mangled names for the 8 entry points"""
+    def syms(path):
+        out = subprocess.check_output(["nm", "-D", "--defined-only", path], text=True)
+        return {l.split()[-1] for l in out.splitlines() if " T " in l and l.split()[-1].startswith("_Z")}
+    ours, ref = syms(ffi.OURS), syms(ffi.REF)
+    wanted = {s for s in ref if re.match(r"_Z\d+(meanshift_gpu|fit_robust_gaussian|collect_p3p_instances|"
+                                        r"solve_batch_p3p_ap3p_gpu|solve_batch_p3p_lambdatwist_gpu|"
+                                        r"optimize_depth_gpu|align_frame_init_gpu|align_frame_eval_gpu)", s)}
+    assert len(wanted) == 8
+    missing = wanted - ours
+    assert not missing, missing
+
+
+def test_python_binding_fails_loudly_without_library(tmp_path, monkeypatch):
+    import voldor_b200.pyvoldor_vo as pv
+
+    monkeypatch.setattr(pv, "_lib", None)
+    monkeypatch.setattr(pv, "_LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError):
+        pv.load_library()

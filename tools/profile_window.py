@@ -1,0 +1,26 @@
+"""Profiling driver: one BASELINE configs[1] window (640x480x8) with a few EM iterations through the public
+binding; meant to be wrapped by ncu (B200_PROFILING.md).  Numbers printed under a profiler are not bench values."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import synth  # noqa: E402
+import voldor_b200  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--iters", type=int, default=4)
+ap.add_argument("--w", type=int, default=640)
+ap.add_argument("--h", type=int, default=480)
+ap.add_argument("--flows", type=int, default=8)
+ap.add_argument("--windows", type=int, default=1)
+a = ap.parse_args()
+win = synth.make_window(a.w, a.h, a.flows, seed=100)
+boot = (win["Rs"][0], win["ts"][0], synth.noisy_depth(win, 0.05, seed=7))
+voldor_b200.set_bootstrap_override(*boot)
+cfg = f"--silent --max_iters {a.iters} --no_trunc_iters 1000 --n_poses_to_sample 8192"
+for _ in range(a.windows):
+    r = voldor_b200.voldor_ex(win["flows"], win["fx"], win["fy"], win["cx"], win["cy"], config=cfg)
+print("n_registered", r["n_registered"], "iters", r["iters"], "stats_ms", r["stats_ms"])

@@ -245,6 +245,16 @@ DLL_EXPORT int vb_optimize_depth_gpu(float** h_flows, float** h_rigidnesses, flo
 }
 
 DLL_EXPORT int vb_set_device(int device) { return (int)cudaSetDevice(device); }
+DLL_EXPORT void vb_profile_enable(int on) {
+    vb::KernelProfile& p = vb::kernel_profile();
+    p.enabled = on != 0;
+    p.search_ms = 0, p.search_launches = 0;
+}
+DLL_EXPORT void vb_profile_get(double* search_ms, long long* search_launches) {
+    vb::KernelProfile& p = vb::kernel_profile();
+    if (search_ms) *search_ms = p.search_ms;
+    if (search_launches) *search_launches = p.search_launches;
+}
 DLL_EXPORT const char* vb_version(void) { return "voldor_b200 0.1 sm_100a"; }
 
 }  // extern "C"

@@ -89,11 +89,11 @@ struct TexStack {
     T* layer(int d) const { return (T*)((char*)ptr + (size_t)d * h * pitch); }
     cudaError_t upload_layer(const T* host, int d, cudaStream_t s) {
         return cudaMemcpy2DAsync(layer(d), pitch, host, (size_t)w * sizeof(T), (size_t)w * sizeof(T), h,
-                                 cudaMemcpyHostToDevice, s);
+                                 cudaMemcpyDefault, s);
     }
     cudaError_t download_layer(T* host, int d, cudaStream_t s) const {
         return cudaMemcpy2DAsync(host, (size_t)w * sizeof(T), layer(d), pitch, (size_t)w * sizeof(T), h,
-                                 cudaMemcpyDeviceToHost, s);
+                                 cudaMemcpyDefault, s);
     }
 };
 
@@ -128,11 +128,11 @@ struct Plane {
     T* layer(int d) const { return ptr + (size_t)d * layer_elems(); }
     cudaError_t upload_layer(const T* host, int d, cudaStream_t s) {
         return cudaMemcpy2DAsync(layer(d), (size_t)pitch * sizeof(T), host, (size_t)w * sizeof(T),
-                                 (size_t)w * sizeof(T), h, cudaMemcpyHostToDevice, s);
+                                 (size_t)w * sizeof(T), h, cudaMemcpyDefault, s);
     }
     cudaError_t download_layer(T* host, int d, cudaStream_t s) const {
         return cudaMemcpy2DAsync(host, (size_t)w * sizeof(T), layer(d), (size_t)pitch * sizeof(T),
-                                 (size_t)w * sizeof(T), h, cudaMemcpyDeviceToHost, s);
+                                 (size_t)w * sizeof(T), h, cudaMemcpyDefault, s);
     }
 };
 

@@ -252,6 +252,113 @@ __global__ void __launch_bounds__(128)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Cooperative candidate cost: the N flow terms and N_dp prior terms of ONE candidate are evaluated by a group
+// of G lanes (one term per lane: the texture fetch and the ~600-instruction Fisk posterior run in parallel),
+// then combined in the reference's order f = 0..N-1, priors 0..N_dp-1 with the same fused multiply-adds, so
+// the result is bit-identical to pixel_cost().  Every lane walks the (cheap) pose chain because the fetch
+// position of frame f depends on the in-view tests of all earlier frames (stale px1 rule).
+// The result is returned on every lane of the group.
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ float pixel_cost_group(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC,
+                                                  int px, int py, float depth, int gl, unsigned gmask, int gbase) {
+    const float fpx = (float)px, fpy = (float)py;
+    const float fw = (float)A.w, fh = (float)A.h;
+    float ox, oy, oz;
+    backproject(C, fpx, fpy, depth, ox, oy, oz);
+    float px1 = fpx, py1 = fpy;
+    float m_px1 = 0, m_py1 = 0, m_px2 = 0, m_py2 = 0;
+    bool my_valid = false;
+    for (int f = 0; f < A.N; f++) {
+        float px2, py2;
+        rigid_move(C.R[f], C.t[f], ox, oy, oz);
+        project(C, ox, oy, oz, px2, py2);
+        if (oz > 0 && px1 >= 0 && px1 < fw && py1 >= 0 && py1 < fh) {
+            if (f == gl) m_px1 = px1, m_py1 = py1, m_px2 = px2, m_py2 = py2, my_valid = true;
+            px1 = px2, py1 = py2;
+        }
+    }
+    float my_w = 0.f, my_log = 0.f;
+    if (my_valid) {
+        const float2 obs = fetch_stack<float2>(A.flows_tex, m_px1, m_py1, gl, A.h);
+        const float rfx = f_sub(m_px2, m_px1), rfy = f_sub(m_py2, m_py1);
+        my_w = A.rig[(size_t)gl * A.plane + (size_t)py * A.pitch + px];
+        my_log = logf(flow_rigidness(rfx, rfy, obs.x, obs.y, A.lambda, A.abs_rf));
+    }
+    const int pf = gl - A.N;
+    if (pf >= 0 && pf < A.N_dp) {
+        backproject(C, fpx, fpy, depth, ox, oy, oz);
+        rigid_move(PC.R[pf], PC.t[pf], ox, oy, oz);
+        project(C, ox, oy, oz, px1, py1);
+        if (oz > 0 && px1 >= 0 && px1 < fw && py1 >= 0 && py1 < fh) {
+            const float target_depth = fetch_stack<float>(A.dp_tex, px1, py1, pf, A.h);
+            const float target_pconf = fetch_stack<float>(A.dp_pconf_tex, px1, py1, pf, A.h);
+            const float target_conf = fetch_stack<float>(A.dp_conf_tex, px1, py1, pf, A.h);
+            if (target_depth > 0) {
+                const float scale = (A.disp_delta > 0 && pf == 0) ? A.disp_delta : A.delta;
+                my_w = f_mul(f_mul(target_pconf, target_conf), scale);
+                my_log = logf(depth_rigidness(oz, target_depth, A.basefocal, A.omega, A.abs_rf));
+                my_valid = true;
+            }
+        }
+    }
+    float cost_sum = 0.f, weight_sum = 0.f;
+    const int terms = A.N + A.N_dp;
+    for (int k = 0; k < terms; k++) {
+        const float w = __shfl_sync(gmask, my_w, gbase + k);
+        const float lg = __shfl_sync(gmask, my_log, gbase + k);
+        const int v = __shfl_sync(gmask, (int)my_valid, gbase + k);
+        if (v) {
+            cost_sum = f_fma(-w, lg, cost_sum);
+            weight_sum = f_add(weight_sum, w);
+        }
+    }
+    if (weight_sum == 0) return INFINITY;
+    return f_div(cost_sum, fmaxf(weight_sum, FLT_EPSILON));
+}
+
+// local propagation with G lanes per chain: block = 128 threads = 128/G chains.
+// chain index c -> (o, seg) with o fastest.
+template <int DIR, int G>
+__global__ void __launch_bounds__(128)
+    k_local_propagation_group(const DepthView A, const __grid_constant__ CamBlock C,
+                              const __grid_constant__ PriorCamBlock PC, int width, int n_other, int n_seg) {
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G;
+    const int gbase = lane - gl;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+    const int chain = (blockIdx.x * 128 + threadIdx.x) / G;
+    if (chain >= n_other * n_seg) return;
+    const int o = chain % n_other, seg = chain / n_other;
+    const bool rowdir = (DIR == DIR_L2R || DIR == DIR_R2L);
+    const int len = rowdir ? A.w : A.h;
+    const int p0 = seg * width;
+    int first, last, step;  // positions visited along the axis, inclusive
+    if (DIR == DIR_L2R || DIR == DIR_T2B) {
+        first = max(1, p0 + 1), last = min(len, p0 + width) - 1, step = 1;
+    } else {
+        first = min(len - 2, p0 + width - 2), last = max(0, p0), step = -1;
+    }
+    const int count = (last - first) * step + 1;
+    if (count <= 0) return;
+    // the candidate for position p is the (possibly just updated) depth of position p - step
+    int sx = rowdir ? first - step : o, sy = rowdir ? o : first - step;
+    float cand = A.depth[(size_t)sy * A.pitch + sx];
+    for (int i = 0, pos = first; i < count; i++, pos += step) {
+        const int x = rowdir ? pos : o, y = rowdir ? o : pos;
+        const size_t idx = (size_t)y * A.pitch + x;
+        const float c = pixel_cost_group<G>(A, C, PC, x, y, cand, gl, gmask, gbase);
+        const float cur_cost = A.cost[idx];
+        if (c < cur_cost) {
+            if (gl == 0) A.depth[idx] = cand, A.cost[idx] = c;
+            // cand stays: it is now this pixel's depth
+        } else {
+            cand = A.depth[idx];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // E-step: rigidness of every flow and confidence of every prior at the current depth
 // (reference: optimize_depth.cu:84-138)
 // ------------------------------------------------------------------------------------------------
@@ -470,12 +577,33 @@ void launch_global(const DepthView& A, const CamBlock& C, const PriorCamBlock& P
         k_global_propagation<DIR><<<dim3(VB_DIV_CEIL(n, 4), VB_DIV_CEIL(other, 32)), dim3(4, 32), 0, s>>>(A, C, PC, step);
 }
 
+template <int DIR, int G>
+void launch_local_group(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC, int width, int other,
+                        int nseg, cudaStream_t s) {
+    const long long threads = (long long)other * nseg * G;
+    k_local_propagation_group<DIR, G><<<(unsigned)VB_DIV_CEIL(threads, 128), 128, 0, s>>>(A, C, PC, width, other, nseg);
+}
+
 template <int DIR>
 void launch_local(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC, int width, cudaStream_t s) {
     const bool rowdir = (DIR == DIR_L2R || DIR == DIR_R2L);
     const int len = rowdir ? A.w : A.h, other = rowdir ? A.h : A.w;
     const int nseg = VB_DIV_CEIL(len, width);
-    k_local_propagation<DIR><<<dim3(VB_DIV_CEIL(other, 32), VB_DIV_CEIL(nseg, 4)), dim3(32, 4), 0, s>>>(A, C, PC, width);
+    const int terms = A.N + A.N_dp;
+    // one lane per likelihood term of a candidate (see pixel_cost_group); a 31-long chain then costs ~1 term of
+    // latency per step instead of N
+    if (terms > 16 && terms <= 32)
+        launch_local_group<DIR, 32>(A, C, PC, width, other, nseg, s);
+    else if (terms > 8 && terms <= 16)
+        launch_local_group<DIR, 16>(A, C, PC, width, other, nseg, s);
+    else if (terms > 4)
+        launch_local_group<DIR, 8>(A, C, PC, width, other, nseg, s);
+    else if (terms > 2)
+        launch_local_group<DIR, 4>(A, C, PC, width, other, nseg, s);
+    else if (terms == 2)
+        launch_local_group<DIR, 2>(A, C, PC, width, other, nseg, s);
+    else
+        k_local_propagation<DIR><<<dim3(VB_DIV_CEIL(other, 32), VB_DIV_CEIL(nseg, 4)), dim3(32, 4), 0, s>>>(A, C, PC, width);
 }
 
 }  // namespace
@@ -554,7 +682,20 @@ int DepthEM::run(int N, int N_dp, const DepthHyper& hp, bool update_rigidness_on
             }
             VB_RETURN_IF_CUDA_ERROR();
         }
+        KernelProfile& prof = kernel_profile();
+        if (prof.enabled) {
+            if (!prof.ev0) cudaEventCreate(&prof.ev0), cudaEventCreate(&prof.ev1);
+            cudaEventRecord(prof.ev0, s);
+        }
         k_cost_and_random_search<<<pg, pb, 0, s>>>(A, cam, pcam, hp.n_rand_samples);
+        if (prof.enabled) {
+            // timing one kernel needs a sync; only done when profiling is switched on
+            cudaEventRecord(prof.ev1, s);
+            cudaEventSynchronize(prof.ev1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, prof.ev0, prof.ev1);
+            prof.search_ms += ms, prof.search_launches++;
+        }
         VB_RETURN_IF_CUDA_ERROR();
         if (hp.global_prop_step > 0) {
             launch_global<DIR_L2R>(A, cam, pcam, hp.global_prop_step, s);
@@ -577,6 +718,11 @@ int DepthEM::run(int N, int N_dp, const DepthHyper& hp, bool update_rigidness_on
 
 DepthEM& global_depth_em() {
     static DepthEM inst;
+    return inst;
+}
+
+KernelProfile& kernel_profile() {
+    static KernelProfile inst;
     return inst;
 }
 

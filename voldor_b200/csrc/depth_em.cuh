@@ -56,4 +56,15 @@ struct DepthEM {
 
 DepthEM& global_depth_em();
 
+// Optional in-library timing of the dominant kernel (fused cost + random search), CUDA events on the launching
+// stream.  Off by default; bench.py switches it on for the roofline figure (vb_profile_* in voldor_b200.h).
+struct KernelProfile {
+    bool enabled = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double search_ms = 0;      // accumulated duration of k_cost_and_random_search
+    long long search_launches = 0;
+    long long launches = 0;    // all kernel launches issued by the depth step / pose stages since reset
+};
+KernelProfile& kernel_profile();
+
 }  // namespace vb

@@ -1,7 +1,13 @@
 // Mean-shift and robust Gaussian fit kernels for sm_100a.  See pose_mode.cuh.
+//
+// Both are single-CTA persistent kernels: the pose pool (<= 8192 x 6 floats = 192 KB) is staged once into
+// shared memory (B200: 227 KB per CTA) and every iteration of the fixed-point loop runs on the device —
+// weights, the reference-ordered tree sums (tree_sum.cuh), the host-side arithmetic of the reference's loop
+// (mean update / displacement test; 6x6 FP64 LU, inverse and shrinkage for the robust fit) and the convergence
+// test — so one launch replaces the reference's up to 100 x (kernel + 2..3 multi-pass reductions + 2..4
+// blocking copies).  Pools that do not fit shared memory are read through L1/L2 instead.
 #include "pose_mode.cuh"
 #include "residual_model.cuh"
-#include "small_linalg.h"
 #include "tree_sum.cuh"
 #include <cmath>
 #include <cstdlib>
@@ -10,9 +16,10 @@ namespace vb {
 
 namespace {
 
-constexpr int kMsThreads = 512;           // 16 warps: one 512-element tree block per warp per round
-constexpr int kMsWarps = kMsThreads / 32;
-constexpr int kMaxTreeBlocks = 512;       // pool size limit 512*512 (two tree levels)
+constexpr int kThreads = 1024;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxTreeBlocks = 512;  // pool size limit 512*512 (two tree levels)
+constexpr size_t kSmemBudget = 225 * 1024;
 
 struct MeanshiftArgs {
     float io_mean[kMeanshiftMaxDims];  // caller's mean: first displacement is measured against it (Q13)
@@ -21,98 +28,139 @@ struct MeanshiftArgs {
     int n_host, dims;
     float kernel_var, epsilon;
     int max_iters;
+    int pool_in_smem, w_in_smem;
+    // optional fused finite-filter of raw hypotheses (reference voldor/geometry.cpp:156-165,191): when rvecs is set
+    // the pool is built here, in hypothesis order, with rvec pre-scaled, and also written to pool_out/used_out
+    const float* rvecs;
+    const float* tvecs;
+    int n_poses;
+    float rvec_scale;
+    float* pool_out;
+    int* used_out;
 };
 
-// weight of sample i around c_mean (reference: meanshift.cu:20-25)
-__device__ __forceinline__ float ms_weight(const float* __restrict__ space, int i, int dims, const float* c_mean,
-                                           float two_var) {
-    float l2 = 0.f;
-    for (int d = 0; d < dims; d++) {
-        const float diff = f_sub(space[(size_t)i * dims + d], c_mean[d]);
-        l2 = f_fma(diff, diff, l2);
+// one tree per (512-block b, quantity q): value(e) supplied by the caller
+template <class Val>
+__device__ __forceinline__ void tree_tasks(int N, int NB, int Q, int warp, int lane, float* partials, Val val) {
+    for (int task = warp; task < NB * Q; task += kWarps) {
+        const int q = task / NB, b = task % NB;
+        const int base = b * 512;
+        const int count = min(512, N - base);
+        float v = tree_sum_512([&](int i) { return val(q, base + i); }, count, lane);
+        if (lane == 0) {
+            if (N == 1) v = val(q, 0);  // the reference launches no reduction at all for a single element
+            partials[q * kMaxTreeBlocks + b] = v;
+        }
     }
-    return expf(f_div(-l2, two_var));
+}
+__device__ __forceinline__ void tree_level2(int NB, int Q, int warp, int lane, const float* partials, float* sums) {
+    for (int q = warp; q < Q; q += kWarps) {
+        const float* p = partials + q * kMaxTreeBlocks;
+        const float v = (NB == 1) ? p[0] : tree_sum_512([&](int i) { return p[i]; }, NB, lane);
+        if (lane == 0) sums[q] = v;
+    }
 }
 
-__global__ void __launch_bounds__(kMsThreads)
-    k_meanshift(const float* __restrict__ space, const int* d_n, const MeanshiftArgs A, float* partials,
+// ------------------------------------------------------------------------------------------------
+// mean-shift (reference: meanshift.cu:12-31 weights, :99-134 host loop)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    k_meanshift(const float* space_in, const int* d_n, const MeanshiftArgs A, float* partials_g, float* w_g,
                 MeanshiftResult* out) {
+    const float* space_g = A.rvecs ? A.pool_out : space_in;  // (no __restrict__: the pool may be built here)
+    extern __shared__ float smem[];
     __shared__ float c_mean[kMeanshiftMaxDims];
     __shared__ float io_mean[kMeanshiftMaxDims];
     __shared__ float sums[kMeanshiftMaxDims + 1];
     __shared__ int done;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int N = d_n ? *d_n : A.n_host;
     const int dims = A.dims;
-    const int Q = dims + 1;
-    if (threadIdx.x < dims) {
-        io_mean[threadIdx.x] = A.io_mean[threadIdx.x];
-        c_mean[threadIdx.x] =
-            (A.center_idx >= 0 && N > 0) ? space[(size_t)A.center_idx * dims + threadIdx.x] : A.io_mean[threadIdx.x];
+    const int Q = A.trial_only ? 1 : dims + 1;
+    __shared__ int s_scan[kWarps];
+    __shared__ int s_total;
+    int N;
+    if (A.rvecs) {
+        // order-preserving compaction: thread t owns hypotheses [t*E, (t+1)*E)
+        const int E = (A.n_poses + kThreads - 1) / kThreads;
+        const int lo = min(A.n_poses, (int)threadIdx.x * E), hi = min(A.n_poses, lo + E);
+        int cnt = 0;
+        for (int i = lo; i < hi; i++) {
+            const float* r = A.rvecs + (size_t)i * 3;
+            const float* tt = A.tvecs + (size_t)i * 3;
+            cnt += isfinite(f_add(f_add(f_add(f_add(f_add(r[0], r[1]), r[2]), tt[0]), tt[1]), tt[2])) ? 1 : 0;
+        }
+        int incl = cnt;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        int base = 0;
+        for (int k = 0; k < warp; k++) base += s_scan[k];
+        if (threadIdx.x == kThreads - 1) s_total = base + incl;
+        int pos = base + incl - cnt;
+        for (int i = lo; i < hi; i++) {
+            const float* r = A.rvecs + (size_t)i * 3;
+            const float* tt = A.tvecs + (size_t)i * 3;
+            if (isfinite(f_add(f_add(f_add(f_add(f_add(r[0], r[1]), r[2]), tt[0]), tt[1]), tt[2]))) {
+                float* o = A.pool_out + (size_t)pos * 6;
+                o[0] = f_mul(r[0], A.rvec_scale), o[1] = f_mul(r[1], A.rvec_scale), o[2] = f_mul(r[2], A.rvec_scale);
+                o[3] = tt[0], o[4] = tt[1], o[5] = tt[2];
+                pos++;
+            }
+        }
+        __syncthreads();
+        N = s_total;
+        if (threadIdx.x == 0) *A.used_out = N;
+    } else {
+        N = d_n ? *d_n : A.n_host;
     }
-    if (threadIdx.x == 0) done = 0;
-    __syncthreads();
     if (N <= 0) {
         if (threadIdx.x == 0) out->used_iters = 0, out->n = N, out->weight_sum = 0.f, out->confidence = 0.f;
         return;
     }
+    // stage the pool
+    const float* space = space_g;
+    float* sm_w = smem;
+    size_t used = 0;
+    if (A.w_in_smem) used = (size_t)((N + 31) / 32 * 32);
+    float* wv = A.w_in_smem ? sm_w : w_g;
+    if (A.pool_in_smem) {
+        float* sp = smem + used;
+        for (int i = threadIdx.x; i < N * dims; i += kThreads) sp[i] = space_g[i];
+        space = sp;
+    }
+    if (threadIdx.x < dims) {
+        io_mean[threadIdx.x] = A.io_mean[threadIdx.x];
+        c_mean[threadIdx.x] =
+            (A.center_idx >= 0) ? space_g[(size_t)A.center_idx * dims + threadIdx.x] : A.io_mean[threadIdx.x];
+    }
+    if (threadIdx.x == 0) done = 0;
+    __syncthreads();
+
     const int NB = (N + 511) / 512;
     const float two_var = f_add(A.kernel_var, A.kernel_var);  // 2*kernel_var
     const int n_iters = A.trial_only ? 1 : A.max_iters;
-    int used = 0;
+    int used_iters = 0;
     float confidence = 0.f, wsum_last = 0.f;
 
     for (int iter = 0; iter < n_iters; iter++) {
-        // level 1: one warp per 512-block, all Q quantities
-        for (int b = warp; b < NB; b += kMsWarps) {
-            const int base = b * 512;
-            const int count = min(512, N - base);
-            float wgt[16];
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const int t = lane + 32 * j;
-                wgt[j] = (t < count) ? ms_weight(space, base + t, dims, c_mean, two_var) : 0.f;
+        // weights w_i = exp(-|x_i - mu|^2 / (2 var))
+        for (int i = threadIdx.x; i < N; i += kThreads) {
+            float l2 = 0.f;
+            for (int d = 0; d < dims; d++) {
+                const float diff = f_sub(space[(size_t)i * dims + d], c_mean[d]);
+                l2 = f_fma(diff, diff, l2);
             }
-            for (int q = 0; q < (A.trial_only ? 1 : Q); q++) {
-                float a[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int t = lane + 32 * j;
-                    float v = 0.f;
-                    if (t < count) {
-                        v = (q == 0) ? wgt[j] : f_mul(wgt[j], space[(size_t)(base + t) * dims + q - 1]);
-                        if (t + 256 < count) {
-                            const float v2 = (q == 0) ? wgt[j + 8]
-                                                      : f_mul(wgt[j + 8], space[(size_t)(base + t + 256) * dims + q - 1]);
-                            v = f_add(v, v2);
-                        }
-                    }
-                    a[j] = v;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; j++) a[j] = f_add(a[j], a[j + 4]);
-                a[0] = f_add(a[0], a[2]);
-                a[1] = f_add(a[1], a[3]);
-                float v = f_add(a[0], a[1]);
-#pragma unroll
-                for (int o = 16; o >= 1; o >>= 1) v = f_add(v, __shfl_down_sync(0xffffffffu, v, o));
-                if (lane == 0) {
-                    if (N == 1) v = (q == 0) ? wgt[0] : f_mul(wgt[0], space[q - 1]);  // no reduction pass at all
-                    partials[(size_t)q * kMaxTreeBlocks + b] = v;
-                }
-            }
+            wv[i] = expf(f_div(-l2, two_var));
         }
         __syncthreads();
-        // level 2: one warp per quantity over the NB block results
-        for (int q = warp; q < (A.trial_only ? 1 : Q); q += kMsWarps) {
-            const float* p = partials + (size_t)q * kMaxTreeBlocks;
-            float v;
-            if (NB == 1)
-                v = p[0];
-            else
-                v = tree_sum_512([&](int i) { return p[i]; }, NB, lane);
-            if (lane == 0) sums[q] = v;
-        }
+        tree_tasks(N, NB, Q, warp, lane, partials_g, [&](int q, int e) {
+            return q == 0 ? wv[e] : f_mul(wv[e], space[(size_t)e * dims + q - 1]);
+        });
+        __syncthreads();
+        tree_level2(NB, Q, warp, lane, partials_g, sums);
         __syncthreads();
         if (threadIdx.x == 0) {
             const float wsum = sums[0];
@@ -122,7 +170,7 @@ __global__ void __launch_bounds__(kMsThreads)
                 float mean_new[kMeanshiftMaxDims];
                 for (int d = 0; d < dims; d++) mean_new[d] = f_div(sums[d + 1], wsum);
                 confidence = f_div(wsum, (float)N);
-                used = iter + 1;
+                used_iters = iter + 1;
                 float disp = 0.f;
                 for (int d = 0; d < dims; d++) {
                     const float df = f_sub(io_mean[d], mean_new[d]);
@@ -140,85 +188,234 @@ __global__ void __launch_bounds__(kMsThreads)
         for (int d = 0; d < dims; d++) out->mean[d] = io_mean[d];
         out->confidence = confidence;
         out->weight_sum = wsum_last;
-        out->used_iters = used;
+        out->used_iters = used_iters;
         out->n = N;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// robust Gaussian: E-step + all weighted sums in one launch (reference: fit_robust_gaussian.cu:56-97,211-242)
+// robust Gaussian fit, whole EM loop on the device
+// (reference: fit_robust_gaussian.cu:56-97 E-step, :160-263 host loop, aux_funs.cpp:101-141 6x6 FP64 helpers)
 // ------------------------------------------------------------------------------------------------
 struct RobustArgs {
     float mean[kRobustMaxDims];
-    float cinv[21];  // lower-triangular packed inverse covariance
-    float trunc_sigma, scale;
-    int N, dims;
+    float covar[21];  // lower-triangular packed start covariance
+    float trunc_sigma, scale, covar_reg_lambda, epsilon;
+    int N, dims, max_iters;
+    int pool_in_smem, w_in_smem;
+};
+struct RobustResult {
+    float mean[kRobustMaxDims];
+    float covar[21];
+    float density;
+    int used_iters;
+    int reliable;
 };
 
-constexpr int kRgThreads = 1024;
-constexpr int kRgWarps = kRgThreads / 32;
+// FP64 helpers with every operation individually rounded (the host code they mirror is compiled without FMA)
+__device__ __forceinline__ double d_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double d_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double d_sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double d_div(double a, double b) { return __ddiv_rn(a, b); }
 
-__global__ void __launch_bounds__(kRgThreads)
-    k_robust_estep(const float* __restrict__ space, const RobustArgs A, float* scratch, float* partials,
-                   float* sums_out) {
+__global__ void __launch_bounds__(kThreads)
+    k_robust_fit(const float* __restrict__ space_g, const RobustArgs A, float* partials_g, float* w_g,
+                 RobustResult* out) {
+    extern __shared__ float smem[];
+    __shared__ float s_mean[kRobustMaxDims];
+    __shared__ float s_cov[21], s_cinv[21];
+    __shared__ float sums[28];
+    __shared__ int s_state;  // 0 continue, 1 converged/reliable, 2 unreliable
+    __shared__ float s_weight;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = A.N, dims = A.dims;
     const int cdims = (dims * dims + dims) / 2;
     const int Q = 1 + dims + cdims;
-    float* W = scratch;                      // [N]
-    float* WS = scratch + N;                 // [N][dims]
-    float* WC = scratch + (size_t)N * (1 + dims);  // [N][cdims]
-
-    for (int idx = threadIdx.x; idx < N; idx += kRgThreads) {
-        float diff[kRobustMaxDims], x[kRobustMaxDims];
-        for (int d = 0; d < dims; d++) {
-            x[d] = f_mul(space[(size_t)idx * dims + d], A.scale);
-            diff[d] = f_sub(x[d], A.mean[d]);
-        }
-        float z = 0.f;
-        for (int d1 = 0; d1 < dims; d1++) {
-            float tmp = 0.f;
-            for (int d2 = 0; d2 < dims; d2++) {
-                const float ci = (d1 >= d2) ? A.cinv[(d1 * d1 + d1) / 2 + d2] : A.cinv[(d2 * d2 + d2) / 2 + d1];
-                tmp = f_add(tmp, f_mul(ci, diff[d2]));
-            }
-            z = f_fma(tmp, diff[d1], z);
-        }
-        z = __fsqrt_rn(z);
-        const float weight = z < A.trunc_sigma ? 1.f : 0.f;  // hard truncation
-        W[idx] = weight;
-        for (int d = 0; d < dims; d++) WS[(size_t)idx * dims + d] = f_mul(weight, x[d]);
-        for (int d1 = 0; d1 < dims; d1++)
-            for (int d2 = 0; d2 <= d1; d2++)
-                WC[(size_t)idx * cdims + (d1 * d1 + d1) / 2 + d2] = f_mul(f_mul(weight, diff[d1]), diff[d2]);
-    }
-    __syncthreads();
-
     const int NB = (N + 511) / 512;
-    for (int task = warp; task < Q * NB; task += kRgWarps) {
-        const int q = task / NB, b = task % NB;
-        const float* src;
-        int stride;
-        if (q == 0)
-            src = W, stride = 1;
-        else if (q <= dims)
-            src = WS + (q - 1), stride = dims;
-        else
-            src = WC + (q - 1 - dims), stride = cdims;
-        const int base = b * 512;
-        const int count = min(512, N - base);
-        float v = tree_sum_512([&](int i) { return src[(size_t)(base + i) * stride]; }, count, lane);
-        if (lane == 0) {
-            if (N == 1) v = src[0];
-            partials[(size_t)q * kMaxTreeBlocks + b] = v;
-        }
+
+    const float* space = space_g;
+    size_t used = 0;
+    if (A.w_in_smem) used = (size_t)((N + 31) / 32 * 32);
+    float* wv = A.w_in_smem ? smem : w_g;
+    if (A.pool_in_smem) {
+        float* sp = smem + used;
+        for (int i = threadIdx.x; i < N * dims; i += kThreads) sp[i] = space_g[i];
+        space = sp;
+    }
+    if (threadIdx.x == 0) {
+        for (int d = 0; d < dims; d++) s_mean[d] = A.mean[d];
+        for (int k = 0; k < cdims; k++) s_cov[k] = A.covar[k];
+        s_weight = 0.f;
+        s_state = 0;
     }
     __syncthreads();
-    for (int q = warp; q < Q; q += kRgWarps) {
-        const float* p = partials + (size_t)q * kMaxTreeBlocks;
-        float v = (NB == 1) ? p[0] : tree_sum_512([&](int i) { return p[i]; }, NB, lane);
-        if (lane == 0) sums_out[q] = v;
+
+    int iter = 0;
+    // 6x6 FP64 scratch of the covariance step: LU with partial pivoting run by the 36 threads (r,c) of the
+    // augmented matrix [a | b] in shared memory — the same operations on the same elements as the sequential host
+    // code it mirrors (aux shim / cv::Matx66d), only issued in parallel
+    __shared__ double sa[36], sb[36], s_inv[36];
+    __shared__ double s_det;
+    __shared__ int s_piv;
+    const int t = threadIdx.x;
+    const int mr = t / 6, mc = t % 6;
+    const bool in_mat = t < 36 && mr < dims && mc < dims;
+    if (t < 36) s_inv[t] = 0.0;
+    for (iter = 0; iter < A.max_iters; iter++) {
+        if (t == 0) {
+            // half -> full (double); shrink towards tr/n * I from the 2nd iteration on
+            for (int d1 = 0; d1 < dims; d1++)
+                for (int d2 = 0; d2 <= d1; d2++) {
+                    sa[d1 * 6 + d2] = (double)s_cov[(d1 * d1 + d1) / 2 + d2];
+                    if (d1 != d2) sa[d2 * 6 + d1] = sa[d1 * 6 + d2];
+                }
+            if (iter > 0 && A.covar_reg_lambda > 0) {
+                const double lambda = (double)A.covar_reg_lambda;
+                double tr = 0;
+                for (int i = 0; i < dims; i++) tr = d_add(tr, sa[i * 6 + i]);
+                const double m = d_div(tr, (double)dims);
+                const double lm = d_mul(lambda, m), oml = d_sub(1.0, lambda);
+                for (int i = 0; i < dims; i++)
+                    for (int j = 0; j < dims; j++)
+                        sa[i * 6 + j] = d_add(d_mul(lm, i == j ? 1.0 : 0.0), d_mul(oml, sa[i * 6 + j]));
+            }
+            // the regularised covariance is what the E-step is documented to use (fit_robust_gaussian.cu:203)
+            for (int d1 = 0; d1 < dims; d1++)
+                for (int d2 = 0; d2 <= d1; d2++) s_cov[(d1 * d1 + d1) / 2 + d2] = (float)sa[d1 * 6 + d2];
+            s_det = 1.0;
+        }
+        if (in_mat) sb[t] = (mr == mc) ? 1.0 : 0.0;
+        __syncthreads();
+        bool singular = false;
+        for (int i = 0; i < dims; i++) {
+            if (t == 0) {
+                int k = i;
+                for (int j = i + 1; j < dims; j++)
+                    if (fabs(sa[j * 6 + i]) > fabs(sa[k * 6 + i])) k = j;
+                s_piv = (fabs(sa[k * 6 + i]) < 2.220446049250313e-16 * 100) ? -1 : k;
+            }
+            __syncthreads();
+            const int k = s_piv;
+            if (k < 0) {
+                singular = true;
+                break;
+            }
+            if (k != i) {
+                if (in_mat && mr == i) {
+                    if (mc >= i) {
+                        const double tmp = sa[i * 6 + mc];
+                        sa[i * 6 + mc] = sa[k * 6 + mc];
+                        sa[k * 6 + mc] = tmp;
+                    }
+                    const double tmp = sb[i * 6 + mc];
+                    sb[i * 6 + mc] = sb[k * 6 + mc];
+                    sb[k * 6 + mc] = tmp;
+                }
+                if (t == 0) s_det = -s_det;
+                __syncthreads();
+            }
+            double na = 0, nb = 0;
+            const bool upd = in_mat && mr > i;
+            if (upd) {
+                const double d = d_div(-1.0, sa[i * 6 + i]);
+                const double alpha = d_mul(sa[mr * 6 + i], d);
+                na = (mc > i) ? d_add(sa[mr * 6 + mc], d_mul(alpha, sa[i * 6 + mc])) : sa[mr * 6 + mc];
+                nb = d_add(sb[mr * 6 + mc], d_mul(alpha, sb[i * 6 + mc]));
+            }
+            __syncthreads();
+            if (upd) sa[mr * 6 + mc] = na, sb[mr * 6 + mc] = nb;
+            if (t == 0) s_det = d_mul(s_det, sa[i * 6 + i]);
+            __syncthreads();
+        }
+        const double det = singular ? 0.0 : s_det;
+        if (det > 0) {  // inverse only written for det > 0 (aux_funs.cpp:104-111)
+            for (int i = dims - 1; i >= 0; i--) {
+                if (t < dims) {
+                    double acc = sb[i * 6 + t];
+                    for (int k = i + 1; k < dims; k++) acc = d_sub(acc, d_mul(sa[i * 6 + k], sb[k * 6 + t]));
+                    sb[i * 6 + t] = d_div(acc, sa[i * 6 + i]);
+                }
+                __syncthreads();
+            }
+            if (in_mat) s_inv[t] = sb[t];
+        }
+        __syncthreads();
+        if (t == 0) {
+            if (det <= 0) {
+                s_state = 2;
+            } else {
+                for (int d1 = 0; d1 < dims; d1++)
+                    for (int d2 = 0; d2 <= d1; d2++) s_cinv[(d1 * d1 + d1) / 2 + d2] = (float)s_inv[d1 * 6 + d2];
+            }
+        }
+        __syncthreads();
+        if (s_state == 2) break;
+
+        // E-step weights: hard truncation of the Mahalanobis distance (fit_robust_gaussian.cu:67-86)
+        for (int i = threadIdx.x; i < N; i += kThreads) {
+            float diff[kRobustMaxDims];
+            for (int d = 0; d < dims; d++) diff[d] = f_sub(f_mul(space[(size_t)i * dims + d], A.scale), s_mean[d]);
+            float z = 0.f;
+            for (int d1 = 0; d1 < dims; d1++) {
+                float tmp = 0.f;
+                for (int d2 = 0; d2 < dims; d2++) {
+                    const float ci = (d1 >= d2) ? s_cinv[(d1 * d1 + d1) / 2 + d2] : s_cinv[(d2 * d2 + d2) / 2 + d1];
+                    tmp = f_add(tmp, f_mul(ci, diff[d2]));
+                }
+                z = f_fma(tmp, diff[d1], z);
+            }
+            z = __fsqrt_rn(z);
+            wv[i] = z < A.trunc_sigma ? 1.f : 0.f;
+        }
+        __syncthreads();
+        // weighted moments, reference tree order
+        tree_tasks(N, NB, Q, warp, lane, partials_g, [&](int q, int e) {
+            const float w = wv[e];
+            if (q == 0) return w;
+            if (q <= dims) return f_mul(w, f_mul(space[(size_t)e * dims + q - 1], A.scale));
+            int k = q - 1 - dims, d1 = 0;
+            while ((d1 + 1) * (d1 + 2) / 2 <= k) d1++;
+            const int d2 = k - (d1 * d1 + d1) / 2;
+            const float a = f_sub(f_mul(space[(size_t)e * dims + d1], A.scale), s_mean[d1]);
+            const float b = f_sub(f_mul(space[(size_t)e * dims + d2], A.scale), s_mean[d2]);
+            return f_mul(f_mul(w, a), b);
+        });
+        __syncthreads();
+        tree_level2(NB, Q, warp, lane, partials_g, sums);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // host part of the reference iteration (fit_robust_gaussian.cu:209-246)
+            const float prev_density = f_div(s_weight, (float)N);
+            const float wsum = sums[0];
+            s_weight = wsum;
+            if (!isfinite(wsum)) {
+                s_state = 2;
+            } else if (fabsf(f_sub(f_div(wsum, (float)N), prev_density)) < A.epsilon) {
+                s_state = 1;  // converged: keep the moments used in this E-step
+            } else {
+                for (int d = 0; d < dims; d++) s_mean[d] = f_div(sums[1 + d], wsum);
+                for (int k = 0; k < cdims; k++) s_cov[k] = f_div(sums[1 + dims + k], wsum);
+            }
+        }
+        __syncthreads();
+        if (s_state != 0) break;
     }
+    if (threadIdx.x == 0) {
+        out->reliable = (s_state != 2);
+        out->used_iters = iter;
+        out->density = f_div(s_weight, (float)N);
+        for (int d = 0; d < dims; d++) out->mean[d] = s_mean[d];
+        for (int k = 0; k < cdims; k++) out->covar[k] = s_cov[k];
+    }
+}
+
+// shared-memory plan: weights first, then the pool, whatever fits
+void smem_plan(int N, int dims, int& pool_in_smem, int& w_in_smem, size_t& bytes) {
+    const size_t wb = (size_t)((N + 31) / 32 * 32) * sizeof(float);
+    const size_t pb = (size_t)N * dims * sizeof(float);
+    w_in_smem = wb <= kSmemBudget;
+    pool_in_smem = w_in_smem && (wb + pb <= kSmemBudget);
+    bytes = (w_in_smem ? wb : 0) + (pool_in_smem ? pb : 0);
 }
 
 }  // namespace
@@ -230,15 +427,26 @@ int PoseMode::init() {
     VB_CUDA(cudaMalloc((void**)&d_result, sizeof(MeanshiftResult)));
     VB_CUDA(cudaMallocHost((void**)&h_result, sizeof(MeanshiftResult)));
     VB_CUDA(cudaMalloc((void**)&d_partials, (size_t)64 * kMaxTreeBlocks * sizeof(float)));
-    VB_CUDA(cudaMalloc((void**)&d_rg_sums, 64 * sizeof(float)));
-    VB_CUDA(cudaMallocHost((void**)&h_rg_sums, 64 * sizeof(float)));
+    VB_CUDA(cudaMalloc((void**)&d_rg_sums, 256));
+    VB_CUDA(cudaMallocHost((void**)&h_rg_sums, 256));
+    VB_CUDA(cudaFuncSetAttribute(k_meanshift, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    VB_CUDA(cudaFuncSetAttribute(k_robust_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    return 0;
+}
+
+static int ensure_w_scratch(PoseMode& M, int N) {
+    if ((size_t)N > M.rg_capacity) {
+        if (M.d_rg_scratch) cudaFree(M.d_rg_scratch);
+        VB_CUDA(cudaMalloc((void**)&M.d_rg_scratch, (size_t)N * sizeof(float)));
+        M.rg_capacity = N;
+    }
     return 0;
 }
 
 int PoseMode::meanshift(const float* d_space, const float* h_space_for_init, const int* d_n, int n_host, int dims,
                         float kernel_var, float* h_io_mean, float* h_o_confidence, int* used_iters,
                         bool use_external_init_mean, float epsilon, int max_iters, int max_init_trials,
-                        float good_init_confidence) {
+                        float good_init_confidence, int n_capacity) {
     (void)h_space_for_init;
     if (int e = init()) return e;
     if (dims > kMeanshiftMaxDims) return (int)cudaErrorInvalidValue;
@@ -258,13 +466,18 @@ int PoseMode::meanshift(const float* d_space, const float* h_space_for_init, con
             N = h_result->n;
         }
         if (N > 512 * 512) return (int)cudaErrorInvalidValue;
+        if (int e = ensure_w_scratch(*this, N)) return e;
+        size_t smem_bytes;
+        smem_plan(N, dims, A.pool_in_smem, A.w_in_smem, smem_bytes);
         float best_conf = 0;
         int best_idx = -1;
         for (int trial = 0; trial < max_init_trials; trial++) {
             const int idx_rand = (rand() % N);
             MeanshiftArgs T = A;
             T.center_idx = idx_rand, T.trial_only = 1, T.n_host = N;
-            k_meanshift<<<1, kMsThreads, 0, stream>>>(d_space, nullptr, T, d_partials, d_result);
+            T.pool_in_smem = 0;  // a single pass does not amortise staging the pool
+            k_meanshift<<<1, kThreads, T.w_in_smem ? (size_t)((N + 31) / 32 * 32) * sizeof(float) : 0, stream>>>(
+                d_space, nullptr, T, d_partials, d_rg_scratch, d_result);
             VB_RETURN_IF_CUDA_ERROR();
             VB_CUDA(cudaMemcpyAsync(h_result, d_result, sizeof(MeanshiftResult), cudaMemcpyDeviceToHost, stream));
             VB_CUDA(cudaStreamSynchronize(stream));
@@ -281,8 +494,44 @@ int PoseMode::meanshift(const float* d_space, const float* h_space_for_init, con
         return (int)cudaErrorInvalidValue;
     }
 
+    // when N lives on the device the shared-memory plan is made for the capacity of the pool
+    const int n_plan = d_n ? n_capacity : N;
+    if (n_plan > 512 * 512) return (int)cudaErrorInvalidValue;
+    if (int e = ensure_w_scratch(*this, n_plan)) return e;
+    size_t smem_bytes;
+    smem_plan(n_plan, dims, A.pool_in_smem, A.w_in_smem, smem_bytes);
+    // layout inside the kernel is derived from the actual N, which is <= n_plan: always fits
+
     if (used_iters) *used_iters = 0;
-    k_meanshift<<<1, kMsThreads, 0, stream>>>(d_space, d_n, A, d_partials, d_result);
+    k_meanshift<<<1, kThreads, smem_bytes, stream>>>(d_space, d_n, A, d_partials, d_rg_scratch, d_result);
+    VB_RETURN_IF_CUDA_ERROR();
+    VB_CUDA(cudaMemcpyAsync(h_result, d_result, sizeof(MeanshiftResult), cudaMemcpyDeviceToHost, stream));
+    VB_CUDA(cudaStreamSynchronize(stream));
+    if (h_result->used_iters > 0) {
+        if (h_o_confidence) *h_o_confidence = h_result->confidence;
+        if (used_iters) *used_iters = h_result->used_iters;
+        for (int d = 0; d < dims; d++) h_io_mean[d] = h_result->mean[d];
+    }
+    return 0;
+}
+
+int PoseMode::meanshift_from_hypotheses(const float* d_rvecs, const float* d_tvecs, int n_poses, float rvec_scale,
+                                        float* d_pool, int* d_used, int dims, float kernel_var, float* h_io_mean,
+                                        float* h_o_confidence, int* used_iters, float epsilon, int max_iters) {
+    if (int e = init()) return e;
+    MeanshiftArgs A;
+    memset(&A, 0, sizeof(A));
+    for (int d = 0; d < dims; d++) A.io_mean[d] = h_io_mean[d];
+    A.n_host = 0, A.dims = dims, A.kernel_var = kernel_var, A.epsilon = epsilon, A.max_iters = max_iters;
+    A.center_idx = -1, A.trial_only = 0;
+    A.rvecs = d_rvecs, A.tvecs = d_tvecs, A.n_poses = n_poses, A.rvec_scale = rvec_scale;
+    A.pool_out = d_pool, A.used_out = d_used;
+    if (n_poses > 512 * 512) return (int)cudaErrorInvalidValue;
+    if (int e = ensure_w_scratch(*this, n_poses)) return e;
+    size_t smem_bytes;
+    smem_plan(n_poses, dims, A.pool_in_smem, A.w_in_smem, smem_bytes);
+    if (used_iters) *used_iters = 0;
+    k_meanshift<<<1, kThreads, smem_bytes, stream>>>(nullptr, nullptr, A, d_partials, d_rg_scratch, d_result);
     VB_RETURN_IF_CUDA_ERROR();
     VB_CUDA(cudaMemcpyAsync(h_result, d_result, sizeof(MeanshiftResult), cudaMemcpyDeviceToHost, stream));
     VB_CUDA(cudaStreamSynchronize(stream));
@@ -299,84 +548,37 @@ int PoseMode::fit_robust_gaussian(const float* d_space, int N, int dims, float s
                                   int* used_iters, float epsilon, int max_iters) {
     if (int e = init()) return e;
     if (dims > kRobustMaxDims) throw;  // reference: fit_robust_gaussian.cu:107-108
-    if (N > 512 * 512) return (int)cudaErrorInvalidValue;
-    const int cdims = (dims * dims + dims) / 2;
-    const int Q = 1 + dims + cdims;
-    const size_t need = (size_t)N * Q;
-    if (need > rg_capacity) {
-        if (d_rg_scratch) cudaFree(d_rg_scratch);
-        VB_CUDA(cudaMalloc((void**)&d_rg_scratch, need * sizeof(float)));
-        rg_capacity = need;
-    }
-
-    float ht_weight = 0;
-    float ht_mean[kRobustMaxDims];
-    float ht_covar[21], ht_covar_inv[21];
-    double covar_full[36], covar_inv_full[36];
-    for (int d = 0; d < dims; d++) ht_mean[d] = h_io_mean[d];
+    if (N > 512 * 512 || N <= 0) return (int)cudaErrorInvalidValue;
+    if (int e = ensure_w_scratch(*this, N)) return e;
+    RobustArgs A;
+    memset(&A, 0, sizeof(A));
+    for (int d = 0; d < dims; d++) A.mean[d] = h_io_mean[d];
     for (int d1 = 0; d1 < dims; d1++)
-        for (int d2 = 0; d2 <= d1; d2++) ht_covar[(d1 * d1 + d1) / 2 + d2] = h_io_covar[d1 * dims + d2];
+        for (int d2 = 0; d2 <= d1; d2++) A.covar[(d1 * d1 + d1) / 2 + d2] = h_io_covar[d1 * dims + d2];
+    A.trunc_sigma = trunc_sigma, A.scale = scale, A.covar_reg_lambda = covar_reg_lambda, A.epsilon = epsilon;
+    A.N = N, A.dims = dims, A.max_iters = max_iters;
+    size_t smem_bytes;
+    smem_plan(N, dims, A.pool_in_smem, A.w_in_smem, smem_bytes);
     if (used_iters) *used_iters = 0;
 
-    int iter;
-    bool reliable = true;
-    for (iter = 0; iter < max_iters; iter++) {
-        // half -> full (double), regularise from the 2nd iteration on, invert (fit_robust_gaussian.cu:166-201)
+    RobustResult* d_res = (RobustResult*)d_rg_sums;
+    RobustResult* h_res = (RobustResult*)h_rg_sums;
+    k_robust_fit<<<1, kThreads, smem_bytes, stream>>>(d_space, A, d_partials, d_rg_scratch, d_res);
+    VB_RETURN_IF_CUDA_ERROR();
+    VB_CUDA(cudaMemcpyAsync(h_res, d_res, sizeof(RobustResult), cudaMemcpyDeviceToHost, stream));
+    VB_CUDA(cudaStreamSynchronize(stream));
+
+    if (h_res->reliable) {
+        if (h_o_density) *h_o_density = h_res->density;
+        if (used_iters) *used_iters = h_res->used_iters;
         for (int d1 = 0; d1 < dims; d1++)
             for (int d2 = 0; d2 <= d1; d2++) {
-                covar_full[d1 * dims + d2] = (double)ht_covar[(d1 * d1 + d1) / 2 + d2];
-                if (d1 != d2) covar_full[d2 * dims + d1] = covar_full[d1 * dims + d2];
-            }
-        if (iter > 0 && covar_reg_lambda > 0) linalg::shrink_to_scaled_identity6(covar_full, covar_reg_lambda, dims);
-        const double det = linalg::inverse6(covar_full, covar_inv_full, dims);
-        if (det <= 0) {
-            reliable = false;
-            break;
-        }
-        for (int d1 = 0; d1 < dims; d1++)
-            for (int d2 = 0; d2 <= d1; d2++) {
-                ht_covar[(d1 * d1 + d1) / 2 + d2] = (float)covar_full[d1 * dims + d2];
-                ht_covar_inv[(d1 * d1 + d1) / 2 + d2] = (float)covar_inv_full[d1 * dims + d2];
-            }
-
-        RobustArgs A;
-        memset(&A, 0, sizeof(A));
-        for (int d = 0; d < dims; d++) A.mean[d] = ht_mean[d];
-        for (int k = 0; k < cdims; k++) A.cinv[k] = ht_covar_inv[k];
-        A.trunc_sigma = trunc_sigma, A.scale = scale, A.N = N, A.dims = dims;
-
-        const float prev_density = ht_weight / N;
-        k_robust_estep<<<1, kRgThreads, 0, stream>>>(d_space, A, d_rg_scratch, d_partials, d_rg_sums);
-        VB_RETURN_IF_CUDA_ERROR();
-        VB_CUDA(cudaMemcpyAsync(h_rg_sums, d_rg_sums, Q * sizeof(float), cudaMemcpyDeviceToHost, stream));
-        VB_CUDA(cudaStreamSynchronize(stream));
-
-        ht_weight = h_rg_sums[0];
-        if (!std::isfinite(ht_weight)) {
-            reliable = false;
-            break;
-        }
-        const float density_change = std::fabs(ht_weight / N - prev_density);
-        if (density_change < epsilon) {
-            reliable = true;
-            break;
-        }
-        // not converged: adopt the new moments (Q15: on convergence the moments USED in the last E-step stay)
-        for (int d = 0; d < dims; d++) ht_mean[d] = h_rg_sums[1 + d] / ht_weight;
-        for (int k = 0; k < cdims; k++) ht_covar[k] = h_rg_sums[1 + dims + k] / ht_weight;
-    }
-
-    if (reliable) {
-        if (h_o_density) *h_o_density = ht_weight / N;
-        if (used_iters) *used_iters = iter;
-        for (int d1 = 0; d1 < dims; d1++)
-            for (int d2 = 0; d2 <= d1; d2++) {
-                h_io_covar[d1 * dims + d2] = ht_covar[(d1 * d1 + d1) / 2 + d2];
+                h_io_covar[d1 * dims + d2] = h_res->covar[(d1 * d1 + d1) / 2 + d2];
                 h_io_covar[d2 * dims + d1] = h_io_covar[d1 * dims + d2];
             }
-        for (int d = 0; d < dims; d++) h_io_mean[d] = ht_mean[d];
+        for (int d = 0; d < dims; d++) h_io_mean[d] = h_res->mean[d];
     }
-    return reliable ? 0 : 1;  // cudaSuccess / !cudaSuccess (fit_robust_gaussian.cu:281-284)
+    return h_res->reliable ? 0 : 1;  // cudaSuccess / !cudaSuccess (fit_robust_gaussian.cu:281-284)
 }
 
 PoseMode& global_pose_mode() {

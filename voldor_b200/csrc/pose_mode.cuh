@@ -29,8 +29,8 @@ struct PoseMode {
     // robust fit scratch
     float* d_rg_scratch = nullptr;
     size_t rg_capacity = 0;
-    float* d_rg_sums = nullptr;
-    float* h_rg_sums = nullptr;  // pinned
+    float* d_rg_sums = nullptr;  // RobustResult on the device
+    float* h_rg_sums = nullptr;  // pinned mirror
 
     int init();
     // Mean-shift on d_space[N][dims]; N is read from d_n when non-null.  Blocks until the result is on the host
@@ -38,7 +38,12 @@ struct PoseMode {
     int meanshift(const float* d_space, const float* h_space_for_init, const int* d_n, int n_host, int dims,
                   float kernel_var, float* h_io_mean, float* h_o_confidence, int* used_iters,
                   bool use_external_init_mean, float epsilon, int max_iters, int max_init_trials,
-                  float good_init_confidence);
+                  float good_init_confidence, int n_capacity = 0);
+    // Successive-pose mean-shift fused with the finite filter of the raw hypotheses: builds the pool
+    // (hypothesis order, rvec * rvec_scale) into d_pool / d_used and iterates on it in the same launch.
+    int meanshift_from_hypotheses(const float* d_rvecs, const float* d_tvecs, int n_poses, float rvec_scale,
+                                  float* d_pool, int* d_used, int dims, float kernel_var, float* h_io_mean,
+                                  float* h_o_confidence, int* used_iters, float epsilon, int max_iters);
     // Robust Gaussian fit on x = scale * d_space (scale folds the caller's pose scaling).
     int fit_robust_gaussian(const float* d_space, int N, int dims, float scale, float* h_io_mean,
                             float* h_io_covar, float trunc_sigma, float covar_reg_lambda, float* h_o_density,

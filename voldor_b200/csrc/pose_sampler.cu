@@ -215,39 +215,41 @@ __global__ void __launch_bounds__(32)
 // order-preserving finite filter of the hypotheses (reference: voldor/geometry.cpp:156-165) fused with the
 // rvec pre-scaling for mean-shift (geometry.cpp:191)
 __global__ void __launch_bounds__(1024)
-    k_filter_pool(const float* rvecs, const float* tvecs, int n_poses, float rvec_scale, float* pool, int* used) {
+    k_filter_pool(const float* __restrict__ rvecs, const float* __restrict__ tvecs, int n_poses, float rvec_scale,
+                  float* pool, int* used) {
+    // each warp owns a contiguous slice; one barrier: slice counts -> slice offsets -> ordered writes
     __shared__ int warp_counts[32];
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int base = 0; base < n_poses; base += 1024) {
-        const int i = base + threadIdx.x;
-        float r0 = quiet_nan(), r1 = 0, r2 = 0, t0 = 0, t1 = 0, t2 = 0;
-        if (i < n_poses) {
-            r0 = rvecs[i * 3], r1 = rvecs[i * 3 + 1], r2 = rvecs[i * 3 + 2];
-            t0 = tvecs[i * 3], t1 = tvecs[i * 3 + 1], t2 = tvecs[i * 3 + 2];
-        }
-        const bool valid = isfinite(f_add(f_add(f_add(f_add(f_add(r0, r1), r2), t0), t1), t2));
-        const unsigned m = __ballot_sync(0xffffffffu, valid);
-        if (lane == 0) warp_counts[wid] = __popc(m);
-        __syncthreads();
-        int rank = carry + __popc(m & ((1u << lane) - 1u));
-        int total = 0;
-        for (int k = 0; k < 32; k++) {
-            if (k < wid) rank += warp_counts[k];
-            total += warp_counts[k];
-        }
-        if (valid) {
-            float* o = pool + (size_t)rank * 6;
-            o[0] = f_mul(r0, rvec_scale), o[1] = f_mul(r1, rvec_scale), o[2] = f_mul(r2, rvec_scale);
-            o[3] = t0, o[4] = t1, o[5] = t2;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) carry += total;
-        __syncthreads();
+    const int per_warp = ((n_poses + 31) / 32 + 31) / 32 * 32;
+    const int begin = wid * per_warp, end = min(n_poses, begin + per_warp);
+    auto is_valid = [&](int i) {
+        if (i >= end) return false;
+        const float r0 = rvecs[i * 3], r1 = rvecs[i * 3 + 1], r2 = rvecs[i * 3 + 2];
+        const float t0 = tvecs[i * 3], t1 = tvecs[i * 3 + 1], t2 = tvecs[i * 3 + 2];
+        return (bool)isfinite(f_add(f_add(f_add(f_add(f_add(r0, r1), r2), t0), t1), t2));
+    };
+    int count = 0;
+    for (int base = begin; base < end; base += 32) count += __popc(__ballot_sync(0xffffffffu, is_valid(base + lane)));
+    if (lane == 0) warp_counts[wid] = count;
+    __syncthreads();
+    int offset = 0, total = 0;
+    for (int k = 0; k < 32; k++) {
+        if (k < wid) offset += warp_counts[k];
+        total += warp_counts[k];
     }
-    if (threadIdx.x == 0) *used = carry;
+    for (int base = begin; base < end; base += 32) {
+        const int i = base + lane;
+        const bool valid = is_valid(i);
+        const unsigned m = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            float* o = pool + (size_t)(offset + __popc(m & ((1u << lane) - 1u))) * 6;
+            o[0] = f_mul(rvecs[i * 3], rvec_scale), o[1] = f_mul(rvecs[i * 3 + 1], rvec_scale);
+            o[2] = f_mul(rvecs[i * 3 + 2], rvec_scale);
+            o[3] = tvecs[i * 3], o[4] = tvecs[i * 3 + 1], o[5] = tvecs[i * 3 + 2];
+        }
+        offset += __popc(m);
+    }
+    if (threadIdx.x == 0) *used = total;
 }
 
 }  // namespace

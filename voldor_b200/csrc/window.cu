@@ -243,7 +243,7 @@ struct Window {
                 VB_CUDA(cudaMalloc((void**)&sc.d_disp, npx * sizeof(float)));
                 sc.disp_cap = npx;
             }
-            VB_CUDA(cudaMemcpyAsync(sc.d_disp, disparity_pt, npx * sizeof(float), cudaMemcpyHostToDevice, s));
+            VB_CUDA(cudaMemcpyAsync(sc.d_disp, disparity_pt, npx * sizeof(float), cudaMemcpyDefault, s));
             k_disparity_to_depth<<<g, b, 0, s>>>(E.dp.layer(0), E.dp.pitch, sc.d_disp, w, h, cfg.basefocal);
             if (disparity_pconf_pt) {
                 VB_CUDA(E.dp_pconf.upload_layer(disparity_pconf_pt, 0, s));
@@ -336,8 +336,10 @@ struct Window {
         if (solve_batch_p3p_device(C.p3c, C.p2c, C.d_count, 0, K[0], K[4], K[2], K[5], sc.rvecs, sc.tvecs,
                                    cfg.n_poses_to_sample, !cfg.lambdatwist, s))
             return -1;
-        if (filter_pose_pool(sc.rvecs, sc.tvecs, cfg.n_poses_to_sample, cfg.meanshift_rvec_scale, sc.pool, sc.d_used, s))
-            return -1;
+        // successive poses: the finite filter of the hypotheses is fused into the mean-shift launch
+        if (!successive_pose)
+            if (filter_pose_pool(sc.rvecs, sc.tvecs, cfg.n_poses_to_sample, cfg.meanshift_rvec_scale, sc.pool, sc.d_used, s))
+                return -1;
 
         float pose_opm[6];
         hm::matrix_to_rvec(cam.R, pose_opm);
@@ -364,9 +366,9 @@ struct Window {
             int ms_iters = cam.last_used_ms_iters;
             float mean_io[6];
             memcpy(mean_io, pose_opm, sizeof(mean_io));
-            if (M.meanshift(sc.pool, nullptr, sc.d_used, 0, 6, cfg.meanshift_kernel_var, mean_io, &density, &ms_iters,
-                            true, cfg.meanshift_epsilon, cfg.meanshift_max_iters, cfg.meanshift_max_init_trials,
-                            cfg.meanshift_good_init_confidence))
+            if (M.meanshift_from_hypotheses(sc.rvecs, sc.tvecs, cfg.n_poses_to_sample, cfg.meanshift_rvec_scale, sc.pool,
+                                            sc.d_used, 6, cfg.meanshift_kernel_var, mean_io, &density, &ms_iters,
+                                            cfg.meanshift_epsilon, cfg.meanshift_max_iters))
                 return -1;
             n_points = sc.h_counts[0];
             pool_used = M.h_result->n;
@@ -505,7 +507,7 @@ struct Window {
         const size_t npx = (size_t)w * h;
         if (depth_pt) {
             k_scale_copy<<<g, b, 0, s>>>(sc.d_out, w, E.depth.ptr, E.depth.pitch, w, h, depth_scale_pending);
-            VB_CUDA(cudaMemcpyAsync(depth_pt, sc.d_out, npx * sizeof(float), cudaMemcpyDeviceToHost, s));
+            VB_CUDA(cudaMemcpyAsync(depth_pt, sc.d_out, npx * sizeof(float), cudaMemcpyDefault, s));
             VB_CUDA(cudaStreamSynchronize(s));
         }
         if (depth_conf_pt) {
@@ -513,7 +515,7 @@ struct Window {
             const float inv_n = (float)(1. / (double)(float)(n_flows + n_depth_priors));
             k_depth_conf<<<g, b, 0, s>>>(sc.d_out, w, h, E.rig.ptr, E.rig.pitch, E.rig.layer_elems(), n_flows,
                                          E.dp_conf.ptr, cp, (size_t)cp * h, n_depth_priors, inv_n);
-            VB_CUDA(cudaMemcpyAsync(depth_conf_pt, sc.d_out, npx * sizeof(float), cudaMemcpyDeviceToHost, s));
+            VB_CUDA(cudaMemcpyAsync(depth_conf_pt, sc.d_out, npx * sizeof(float), cudaMemcpyDefault, s));
             VB_CUDA(cudaStreamSynchronize(s));
         }
         VB_RETURN_IF_CUDA_ERROR();
