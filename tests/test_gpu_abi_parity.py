@@ -236,3 +236,39 @@ def test_fit_robust_gaussian_unreliable(libs):
         rc, m, v, d, u = lib.fit_robust_gaussian(pool, mode, cov0)
         assert rc == 1
         assert np.array_equal(m, mode) and np.array_equal(v, cov0)
+
+
+def _align_inputs(w, h, N, seed):
+    rng = np.random.default_rng(seed)
+    win = synth.make_window(w, h, N, seed=seed)
+    depths = np.stack([win["depth_gt"] * (1 + 0.02 * i) for i in range(N)]).astype(np.float32)
+    yy, xx = np.mgrid[0:h, 0:w]
+    images = np.stack([0.5 + 0.3 * np.sin(xx / 9.0 + i) * np.cos(yy / 7.0) for i in range(N)]).astype(np.float32)
+    weights = rng.uniform(0.5, 1.0, (N, h, w)).astype(np.float32)
+    return win, images, depths, weights
+
+
+@pytest.mark.parametrize("crw", [0.0, 0.5])
+def test_align_frame_parity(libs, crw):
+    """frame-alignment residual/Jacobian: identical NaN pattern, <= 1e-4 relative"""
+    mine, ref = libs
+    w, h, N = 96, 64, 3
+    win, images, depths, weights = _align_inputs(w, h, N, 13)
+    outs = []
+    p_ref = np.array([0.01, -0.02, 0.005, 0.05, 0.02, 0.1, 0.01, 0.02, -0.01], np.float32)
+    p_tar = np.array([-0.005, 0.01, 0.0, 0.0, 0.01, -0.05, 0.0, -0.01, 0.02], np.float32)
+    for lib in (mine, ref):
+        assert lib.align_init(images, depths, weights, win["K"], 40.0, crw) == 0
+        rc, res, jac = lib.align_eval(0, 1, p_ref, p_tar, w, h, True)
+        assert rc == 0
+        rc, res2, jac2 = lib.align_eval(2, 0, np.zeros(9, np.float32), p_tar, w, h, False)
+        assert rc == 0
+        outs.append((res, jac, res2, jac2))
+    for k, (a, b) in enumerate(zip(*outs)):
+        rep = ffi.mismatch_report(a, b, f"align_frame crw={crw} out{k}")
+        _report(rep)
+        assert rep["nan_pattern_equal"], rep
+        fin = np.isfinite(b)
+        scale = np.maximum(np.abs(b[fin]), 1e-3 * np.abs(b[fin]).max())
+        assert (np.abs(a[fin] - b[fin]) / scale).max() <= 1e-4, rep
+    assert np.isfinite(outs[1][0]).mean() > 0.5

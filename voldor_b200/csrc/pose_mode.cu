@@ -1,62 +1,158 @@
 // Mean-shift and robust Gaussian fit kernels for sm_100a.  See pose_mode.cuh.
 //
-// Both are single-CTA persistent kernels: the pose pool (<= 8192 x 6 floats = 192 KB) is staged once into
-// shared memory (B200: 227 KB per CTA) and every iteration of the fixed-point loop runs on the device —
-// weights, the reference-ordered tree sums (tree_sum.cuh), the host-side arithmetic of the reference's loop
-// (mean update / displacement test; 6x6 FP64 LU, inverse and shrinkage for the robust fit) and the convergence
-// test — so one launch replaces the reference's up to 100 x (kernel + 2..3 multi-pass reductions + 2..4
-// blocking copies).  Pools that do not fit shared memory are read through L1/L2 instead.
+// Both run as ONE launch of ONE thread-block cluster (8 CTAs x 512 threads, distributed over 8 SMs): the pose
+// pool (<= 8192 x 6 floats) is split by 512-element tree blocks over the CTAs and staged in their shared memory;
+// every iteration of the fixed-point loop runs on the device — weights, the reference-ordered tree sums
+// (tree_sum.cuh; level-1 partials are exchanged through L2 with one hardware cluster barrier per iteration,
+// double buffered), the host-side arithmetic of the reference's loop (mean update / displacement test; 6x6 FP64
+// LU, inverse and shrinkage for the robust fit — evaluated redundantly and identically by every CTA) and the
+// convergence test.  One launch replaces the reference's up to 100 x (kernel + 2..3 multi-pass reductions +
+// 2..4 blocking copies) per call.
 #include "pose_mode.cuh"
 #include "residual_model.cuh"
 #include "tree_sum.cuh"
 #include <cmath>
+#include <cooperative_groups.h>
 #include <cstdlib>
+
+namespace cg = cooperative_groups;
 
 namespace vb {
 
 namespace {
 
-constexpr int kThreads = 1024;
+constexpr int kCluster = 8;
+constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxTreeBlocks = 512;  // pool size limit 512*512 (two tree levels)
-constexpr size_t kSmemBudget = 225 * 1024;
+constexpr size_t kSmemBudget = 200 * 1024;
 
-struct MeanshiftArgs {
-    float io_mean[kMeanshiftMaxDims];  // caller's mean: first displacement is measured against it (Q13)
-    int center_idx;                    // >= 0: start from space[center_idx]; < 0: start from io_mean
-    int trial_only;                    // 1: only the kernel-weight sum around the start point
-    int n_host, dims;
-    float kernel_var, epsilon;
-    int max_iters;
-    int pool_in_smem, w_in_smem;
-    // optional fused finite-filter of raw hypotheses (reference voldor/geometry.cpp:156-165,191): when rvecs is set
-    // the pool is built here, in hypothesis order, with rvec pre-scaled, and also written to pool_out/used_out
-    const float* rvecs;
+struct PoolSource {
+    // either a ready pool (space + n from device or host) or raw hypotheses to filter first
+    const float* space;
+    const int* d_n;
+    int n_host;
+    const float* rvecs;  // optional fused finite-filter (reference voldor/geometry.cpp:156-165,191)
     const float* tvecs;
     int n_poses;
     float rvec_scale;
     float* pool_out;
     int* used_out;
+    int* cta_counts;  // [kCluster] scratch
 };
 
-// one tree per (512-block b, quantity q): value(e) supplied by the caller
+struct MeanshiftArgs {
+    float io_mean[kMeanshiftMaxDims];  // caller's mean: first displacement is measured against it (Q13)
+    int center_idx;                    // >= 0: start from space[center_idx]; < 0: start from io_mean
+    int trial_only;                    // 1: only the kernel-weight sum around the start point
+    int dims;
+    float kernel_var, epsilon;
+    int max_iters;
+    int slice_in_smem;
+    PoolSource src;
+};
+
+// Ordered compaction of finite hypotheses across the whole cluster; returns the pool size on every thread.
+__device__ int build_pool(const PoolSource& S, cg::cluster_group& cluster, int rank) {
+    __shared__ int s_scan[kWarps];
+    __shared__ int s_base, s_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gid = rank * kThreads + threadIdx.x;
+    const int E = (S.n_poses + kCluster * kThreads - 1) / (kCluster * kThreads);
+    const int lo = min(S.n_poses, gid * E), hi = min(S.n_poses, lo + E);
+    auto valid = [&](int i) {
+        const float* r = S.rvecs + (size_t)i * 3;
+        const float* t = S.tvecs + (size_t)i * 3;
+        return (bool)isfinite(f_add(f_add(f_add(f_add(f_add(r[0], r[1]), r[2]), t[0]), t[1]), t[2]));
+    };
+    int cnt = 0;
+    for (int i = lo; i < hi; i++) cnt += valid(i) ? 1 : 0;
+    int incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int k = 0; k < warp; k++) base += s_scan[k];
+    if (threadIdx.x == kThreads - 1) {
+        S.cta_counts[rank] = base + incl;
+        __threadfence();
+    }
+    cluster.sync();
+    if (threadIdx.x == 0) {
+        int b = 0, tot = 0;
+        for (int k = 0; k < kCluster; k++) {
+            const int c = ((volatile int*)S.cta_counts)[k];
+            if (k < rank) b += c;
+            tot += c;
+        }
+        s_base = b, s_total = tot;
+    }
+    __syncthreads();
+    int pos = s_base + base + incl - cnt;
+    for (int i = lo; i < hi; i++) {
+        if (valid(i)) {
+            const float* r = S.rvecs + (size_t)i * 3;
+            const float* t = S.tvecs + (size_t)i * 3;
+            float* o = S.pool_out + (size_t)pos * 6;
+            o[0] = f_mul(r[0], S.rvec_scale), o[1] = f_mul(r[1], S.rvec_scale), o[2] = f_mul(r[2], S.rvec_scale);
+            o[3] = t[0], o[4] = t[1], o[5] = t[2];
+            pos++;
+        }
+    }
+    __threadfence();
+    cluster.sync();
+    if (rank == 0 && threadIdx.x == 0) *S.used_out = s_total;
+    return s_total;
+}
+
+// element bookkeeping of one CTA: it owns tree blocks b = rank, rank+8, ... ; local block lb = b / 8
+struct Slice {
+    int N, NB, nlb, rank, dims;
+    const float* global;  // pool in global memory
+    const float* local;   // staged slice (or nullptr)
+    __device__ __forceinline__ int gidx(int li) const { return ((li >> 9) * kCluster + rank) * 512 + (li & 511); }
+    __device__ __forceinline__ float x(int li, int d) const {
+        return local ? local[(size_t)li * dims + d] : ((const volatile float*)global)[(size_t)gidx(li) * dims + d];
+    }
+};
+
+__device__ void stage_slice(Slice& S, float* smem_pool, bool in_smem) {
+    S.local = nullptr;
+    if (!in_smem) return;
+    const int n_local = S.nlb * 512;
+    for (int k = threadIdx.x; k < n_local * S.dims; k += kThreads) {
+        const int li = k / S.dims, d = k - li * S.dims;
+        const int g = S.gidx(li);
+        smem_pool[k] = (g < S.N) ? ((const volatile float*)S.global)[(size_t)g * S.dims + d] : 0.f;
+    }
+    S.local = smem_pool;
+}
+
+// level 1: one warp per (local tree block, quantity); level 2: one warp per quantity (every CTA, redundantly)
 template <class Val>
-__device__ __forceinline__ void tree_tasks(int N, int NB, int Q, int warp, int lane, float* partials, Val val) {
-    for (int task = warp; task < NB * Q; task += kWarps) {
-        const int q = task / NB, b = task % NB;
-        const int base = b * 512;
-        const int count = min(512, N - base);
-        float v = tree_sum_512([&](int i) { return val(q, base + i); }, count, lane);
+__device__ __forceinline__ void tree_level1(const Slice& S, int Q, float* partials, Val val) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int task = warp; task < S.nlb * Q; task += kWarps) {
+        const int q = task / S.nlb, lb = task % S.nlb;
+        const int b = lb * kCluster + S.rank;
+        if (b >= S.NB) continue;
+        const int count = min(512, S.N - b * 512);
+        float v = tree_sum_512([&](int i) { return val(q, lb * 512 + i); }, count, lane);
         if (lane == 0) {
-            if (N == 1) v = val(q, 0);  // the reference launches no reduction at all for a single element
+            if (S.N == 1) v = val(q, 0);  // the reference launches no reduction at all for a single element
             partials[q * kMaxTreeBlocks + b] = v;
         }
     }
 }
-__device__ __forceinline__ void tree_level2(int NB, int Q, int warp, int lane, const float* partials, float* sums) {
+__device__ __forceinline__ void tree_level2(int NB, int Q, const float* partials, float* sums) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const volatile float* pv = partials;
     for (int q = warp; q < Q; q += kWarps) {
-        const float* p = partials + q * kMaxTreeBlocks;
-        const float v = (NB == 1) ? p[0] : tree_sum_512([&](int i) { return p[i]; }, NB, lane);
+        const volatile float* p = pv + q * kMaxTreeBlocks;
+        const float v = (NB == 1) ? p[0] : tree_sum_512([&](int i) { return (float)p[i]; }, NB, lane);
         if (lane == 0) sums[q] = v;
     }
 }
@@ -64,103 +160,70 @@ __device__ __forceinline__ void tree_level2(int NB, int Q, int warp, int lane, c
 // ------------------------------------------------------------------------------------------------
 // mean-shift (reference: meanshift.cu:12-31 weights, :99-134 host loop)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-    k_meanshift(const float* space_in, const int* d_n, const MeanshiftArgs A, float* partials_g, float* w_g,
-                MeanshiftResult* out) {
-    const float* space_g = A.rvecs ? A.pool_out : space_in;  // (no __restrict__: the pool may be built here)
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
+    k_meanshift(const MeanshiftArgs A, float* partials_g, MeanshiftResult* out) {
     extern __shared__ float smem[];
     __shared__ float c_mean[kMeanshiftMaxDims];
     __shared__ float io_mean[kMeanshiftMaxDims];
     __shared__ float sums[kMeanshiftMaxDims + 1];
     __shared__ int done;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
     const int dims = A.dims;
     const int Q = A.trial_only ? 1 : dims + 1;
-    __shared__ int s_scan[kWarps];
-    __shared__ int s_total;
+
     int N;
-    if (A.rvecs) {
-        // order-preserving compaction: thread t owns hypotheses [t*E, (t+1)*E)
-        const int E = (A.n_poses + kThreads - 1) / kThreads;
-        const int lo = min(A.n_poses, (int)threadIdx.x * E), hi = min(A.n_poses, lo + E);
-        int cnt = 0;
-        for (int i = lo; i < hi; i++) {
-            const float* r = A.rvecs + (size_t)i * 3;
-            const float* tt = A.tvecs + (size_t)i * 3;
-            cnt += isfinite(f_add(f_add(f_add(f_add(f_add(r[0], r[1]), r[2]), tt[0]), tt[1]), tt[2])) ? 1 : 0;
-        }
-        int incl = cnt;
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (lane == 31) s_scan[warp] = incl;
-        __syncthreads();
-        int base = 0;
-        for (int k = 0; k < warp; k++) base += s_scan[k];
-        if (threadIdx.x == kThreads - 1) s_total = base + incl;
-        int pos = base + incl - cnt;
-        for (int i = lo; i < hi; i++) {
-            const float* r = A.rvecs + (size_t)i * 3;
-            const float* tt = A.tvecs + (size_t)i * 3;
-            if (isfinite(f_add(f_add(f_add(f_add(f_add(r[0], r[1]), r[2]), tt[0]), tt[1]), tt[2]))) {
-                float* o = A.pool_out + (size_t)pos * 6;
-                o[0] = f_mul(r[0], A.rvec_scale), o[1] = f_mul(r[1], A.rvec_scale), o[2] = f_mul(r[2], A.rvec_scale);
-                o[3] = tt[0], o[4] = tt[1], o[5] = tt[2];
-                pos++;
-            }
-        }
-        __syncthreads();
-        N = s_total;
-        if (threadIdx.x == 0) *A.used_out = N;
+    const float* space_g = A.src.space;
+    if (A.src.rvecs) {
+        N = build_pool(A.src, cluster, rank);
+        space_g = A.src.pool_out;
     } else {
-        N = d_n ? *d_n : A.n_host;
+        N = A.src.d_n ? *A.src.d_n : A.src.n_host;
     }
     if (N <= 0) {
-        if (threadIdx.x == 0) out->used_iters = 0, out->n = N, out->weight_sum = 0.f, out->confidence = 0.f;
+        if (rank == 0 && threadIdx.x == 0) out->used_iters = 0, out->n = N, out->weight_sum = 0.f, out->confidence = 0.f;
         return;
     }
-    // stage the pool
-    const float* space = space_g;
-    float* sm_w = smem;
-    size_t used = 0;
-    if (A.w_in_smem) used = (size_t)((N + 31) / 32 * 32);
-    float* wv = A.w_in_smem ? sm_w : w_g;
-    if (A.pool_in_smem) {
-        float* sp = smem + used;
-        for (int i = threadIdx.x; i < N * dims; i += kThreads) sp[i] = space_g[i];
-        space = sp;
-    }
+    Slice S;
+    S.N = N, S.NB = (N + 511) / 512, S.rank = rank, S.dims = dims, S.global = space_g;
+    S.nlb = (S.NB - rank + kCluster - 1) / kCluster;
+    if (S.nlb < 0) S.nlb = 0;
+    float* wv = smem;  // weights of the local slice
+    stage_slice(S, smem + (size_t)S.nlb * 512, A.slice_in_smem != 0);
     if (threadIdx.x < dims) {
         io_mean[threadIdx.x] = A.io_mean[threadIdx.x];
-        c_mean[threadIdx.x] =
-            (A.center_idx >= 0) ? space_g[(size_t)A.center_idx * dims + threadIdx.x] : A.io_mean[threadIdx.x];
+        c_mean[threadIdx.x] = (A.center_idx >= 0)
+                                  ? ((const volatile float*)space_g)[(size_t)A.center_idx * dims + threadIdx.x]
+                                  : A.io_mean[threadIdx.x];
     }
     if (threadIdx.x == 0) done = 0;
     __syncthreads();
 
-    const int NB = (N + 511) / 512;
     const float two_var = f_add(A.kernel_var, A.kernel_var);  // 2*kernel_var
     const int n_iters = A.trial_only ? 1 : A.max_iters;
     int used_iters = 0;
     float confidence = 0.f, wsum_last = 0.f;
 
     for (int iter = 0; iter < n_iters; iter++) {
-        // weights w_i = exp(-|x_i - mu|^2 / (2 var))
-        for (int i = threadIdx.x; i < N; i += kThreads) {
-            float l2 = 0.f;
-            for (int d = 0; d < dims; d++) {
-                const float diff = f_sub(space[(size_t)i * dims + d], c_mean[d]);
-                l2 = f_fma(diff, diff, l2);
+        float* partials = partials_g + (size_t)(iter & 1) * 32 * kMaxTreeBlocks;
+        // weights w_i = exp(-|x_i - mu|^2 / (2 var)) of the local slice
+        for (int li = threadIdx.x; li < S.nlb * 512; li += kThreads) {
+            float wgt = 0.f;
+            if (S.gidx(li) < N) {
+                float l2 = 0.f;
+                for (int d = 0; d < dims; d++) {
+                    const float diff = f_sub(S.x(li, d), c_mean[d]);
+                    l2 = f_fma(diff, diff, l2);
+                }
+                wgt = expf(f_div(-l2, two_var));
             }
-            wv[i] = expf(f_div(-l2, two_var));
+            wv[li] = wgt;
         }
         __syncthreads();
-        tree_tasks(N, NB, Q, warp, lane, partials_g, [&](int q, int e) {
-            return q == 0 ? wv[e] : f_mul(wv[e], space[(size_t)e * dims + q - 1]);
-        });
-        __syncthreads();
-        tree_level2(NB, Q, warp, lane, partials_g, sums);
+        tree_level1(S, Q, partials, [&](int q, int li) { return q == 0 ? wv[li] : f_mul(wv[li], S.x(li, q - 1)); });
+        __threadfence();
+        cluster.sync();
+        tree_level2(S.NB, Q, partials, sums);
         __syncthreads();
         if (threadIdx.x == 0) {
             const float wsum = sums[0];
@@ -184,7 +247,7 @@ __global__ void __launch_bounds__(kThreads)
         __syncthreads();
         if (done) break;
     }
-    if (threadIdx.x == 0) {
+    if (rank == 0 && threadIdx.x == 0) {
         for (int d = 0; d < dims; d++) out->mean[d] = io_mean[d];
         out->confidence = confidence;
         out->weight_sum = wsum_last;
@@ -202,7 +265,8 @@ struct RobustArgs {
     float covar[21];  // lower-triangular packed start covariance
     float trunc_sigma, scale, covar_reg_lambda, epsilon;
     int N, dims, max_iters;
-    int pool_in_smem, w_in_smem;
+    int slice_in_smem;
+    const float* space;
 };
 struct RobustResult {
     float mean[kRobustMaxDims];
@@ -218,50 +282,47 @@ __device__ __forceinline__ double d_add(double a, double b) { return __dadd_rn(a
 __device__ __forceinline__ double d_sub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double d_div(double a, double b) { return __ddiv_rn(a, b); }
 
-__global__ void __launch_bounds__(kThreads)
-    k_robust_fit(const float* __restrict__ space_g, const RobustArgs A, float* partials_g, float* w_g,
-                 RobustResult* out) {
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
+    k_robust_fit(const RobustArgs A, float* partials_g, RobustResult* out) {
     extern __shared__ float smem[];
     __shared__ float s_mean[kRobustMaxDims];
     __shared__ float s_cov[21], s_cinv[21];
     __shared__ float sums[28];
     __shared__ int s_state;  // 0 continue, 1 converged/reliable, 2 unreliable
     __shared__ float s_weight;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int N = A.N, dims = A.dims;
-    const int cdims = (dims * dims + dims) / 2;
-    const int Q = 1 + dims + cdims;
-    const int NB = (N + 511) / 512;
-
-    const float* space = space_g;
-    size_t used = 0;
-    if (A.w_in_smem) used = (size_t)((N + 31) / 32 * 32);
-    float* wv = A.w_in_smem ? smem : w_g;
-    if (A.pool_in_smem) {
-        float* sp = smem + used;
-        for (int i = threadIdx.x; i < N * dims; i += kThreads) sp[i] = space_g[i];
-        space = sp;
-    }
-    if (threadIdx.x == 0) {
-        for (int d = 0; d < dims; d++) s_mean[d] = A.mean[d];
-        for (int k = 0; k < cdims; k++) s_cov[k] = A.covar[k];
-        s_weight = 0.f;
-        s_state = 0;
-    }
-    __syncthreads();
-
-    int iter = 0;
     // 6x6 FP64 scratch of the covariance step: LU with partial pivoting run by the 36 threads (r,c) of the
     // augmented matrix [a | b] in shared memory — the same operations on the same elements as the sequential host
     // code it mirrors (aux shim / cv::Matx66d), only issued in parallel
     __shared__ double sa[36], sb[36], s_inv[36];
     __shared__ double s_det;
     __shared__ int s_piv;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int N = A.N, dims = A.dims;
+    const int cdims = (dims * dims + dims) / 2;
+    const int Q = 1 + dims + cdims;
+
+    Slice S;
+    S.N = N, S.NB = (N + 511) / 512, S.rank = rank, S.dims = dims, S.global = A.space;
+    S.nlb = (S.NB - rank + kCluster - 1) / kCluster;
+    if (S.nlb < 0) S.nlb = 0;
+    float* wv = smem;
+    stage_slice(S, smem + (size_t)S.nlb * 512, A.slice_in_smem != 0);
     const int t = threadIdx.x;
+    if (t == 0) {
+        for (int d = 0; d < dims; d++) s_mean[d] = A.mean[d];
+        for (int k = 0; k < cdims; k++) s_cov[k] = A.covar[k];
+        s_weight = 0.f;
+        s_state = 0;
+    }
     const int mr = t / 6, mc = t % 6;
     const bool in_mat = t < 36 && mr < dims && mc < dims;
     if (t < 36) s_inv[t] = 0.0;
+    __syncthreads();
+
+    int iter = 0;
     for (iter = 0; iter < A.max_iters; iter++) {
+        float* partials = partials_g + (size_t)(iter & 1) * 32 * kMaxTreeBlocks;
         if (t == 0) {
             // half -> full (double); shrink towards tr/n * I from the 2nd iteration on
             for (int d1 = 0; d1 < dims; d1++)
@@ -279,7 +340,7 @@ __global__ void __launch_bounds__(kThreads)
                     for (int j = 0; j < dims; j++)
                         sa[i * 6 + j] = d_add(d_mul(lm, i == j ? 1.0 : 0.0), d_mul(oml, sa[i * 6 + j]));
             }
-            // the regularised covariance is what the E-step is documented to use (fit_robust_gaussian.cu:203)
+            // the regularised covariance is the one reported on convergence (fit_robust_gaussian.cu:203)
             for (int d1 = 0; d1 < dims; d1++)
                 for (int d2 = 0; d2 <= d1; d2++) s_cov[(d1 * d1 + d1) / 2 + d2] = (float)sa[d1 * 6 + d2];
             s_det = 1.0;
@@ -352,38 +413,43 @@ __global__ void __launch_bounds__(kThreads)
         if (s_state == 2) break;
 
         // E-step weights: hard truncation of the Mahalanobis distance (fit_robust_gaussian.cu:67-86)
-        for (int i = threadIdx.x; i < N; i += kThreads) {
-            float diff[kRobustMaxDims];
-            for (int d = 0; d < dims; d++) diff[d] = f_sub(f_mul(space[(size_t)i * dims + d], A.scale), s_mean[d]);
-            float z = 0.f;
-            for (int d1 = 0; d1 < dims; d1++) {
-                float tmp = 0.f;
-                for (int d2 = 0; d2 < dims; d2++) {
-                    const float ci = (d1 >= d2) ? s_cinv[(d1 * d1 + d1) / 2 + d2] : s_cinv[(d2 * d2 + d2) / 2 + d1];
-                    tmp = f_add(tmp, f_mul(ci, diff[d2]));
+        for (int li = t; li < S.nlb * 512; li += kThreads) {
+            float wgt = 0.f;
+            if (S.gidx(li) < N) {
+                float diff[kRobustMaxDims];
+                for (int d = 0; d < dims; d++) diff[d] = f_sub(f_mul(S.x(li, d), A.scale), s_mean[d]);
+                float z = 0.f;
+                for (int d1 = 0; d1 < dims; d1++) {
+                    float tmp = 0.f;
+                    for (int d2 = 0; d2 < dims; d2++) {
+                        const float ci = (d1 >= d2) ? s_cinv[(d1 * d1 + d1) / 2 + d2] : s_cinv[(d2 * d2 + d2) / 2 + d1];
+                        tmp = f_add(tmp, f_mul(ci, diff[d2]));
+                    }
+                    z = f_fma(tmp, diff[d1], z);
                 }
-                z = f_fma(tmp, diff[d1], z);
+                z = __fsqrt_rn(z);
+                wgt = z < A.trunc_sigma ? 1.f : 0.f;
             }
-            z = __fsqrt_rn(z);
-            wv[i] = z < A.trunc_sigma ? 1.f : 0.f;
+            wv[li] = wgt;
         }
         __syncthreads();
         // weighted moments, reference tree order
-        tree_tasks(N, NB, Q, warp, lane, partials_g, [&](int q, int e) {
-            const float w = wv[e];
+        tree_level1(S, Q, partials, [&](int q, int li) {
+            const float w = wv[li];
             if (q == 0) return w;
-            if (q <= dims) return f_mul(w, f_mul(space[(size_t)e * dims + q - 1], A.scale));
+            if (q <= dims) return f_mul(w, f_mul(S.x(li, q - 1), A.scale));
             int k = q - 1 - dims, d1 = 0;
             while ((d1 + 1) * (d1 + 2) / 2 <= k) d1++;
             const int d2 = k - (d1 * d1 + d1) / 2;
-            const float a = f_sub(f_mul(space[(size_t)e * dims + d1], A.scale), s_mean[d1]);
-            const float b = f_sub(f_mul(space[(size_t)e * dims + d2], A.scale), s_mean[d2]);
+            const float a = f_sub(f_mul(S.x(li, d1), A.scale), s_mean[d1]);
+            const float b = f_sub(f_mul(S.x(li, d2), A.scale), s_mean[d2]);
             return f_mul(f_mul(w, a), b);
         });
+        __threadfence();
+        cluster.sync();
+        tree_level2(S.NB, Q, partials, sums);
         __syncthreads();
-        tree_level2(NB, Q, warp, lane, partials_g, sums);
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        if (t == 0) {
             // host part of the reference iteration (fit_robust_gaussian.cu:209-246)
             const float prev_density = f_div(s_weight, (float)N);
             const float wsum = sums[0];
@@ -400,7 +466,7 @@ __global__ void __launch_bounds__(kThreads)
         __syncthreads();
         if (s_state != 0) break;
     }
-    if (threadIdx.x == 0) {
+    if (rank == 0 && t == 0) {
         out->reliable = (s_state != 2);
         out->used_iters = iter;
         out->density = f_div(s_weight, (float)N);
@@ -409,13 +475,14 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
-// shared-memory plan: weights first, then the pool, whatever fits
-void smem_plan(int N, int dims, int& pool_in_smem, int& w_in_smem, size_t& bytes) {
-    const size_t wb = (size_t)((N + 31) / 32 * 32) * sizeof(float);
-    const size_t pb = (size_t)N * dims * sizeof(float);
-    w_in_smem = wb <= kSmemBudget;
-    pool_in_smem = w_in_smem && (wb + pb <= kSmemBudget);
-    bytes = (w_in_smem ? wb : 0) + (pool_in_smem ? pb : 0);
+// shared-memory plan for a pool of at most n elements: weights + (if it fits) the slice of every CTA
+void smem_plan(int n, int dims, int& slice_in_smem, size_t& bytes) {
+    const int NB = (n + 511) / 512;
+    const size_t nlb = (size_t)(NB + kCluster - 1) / kCluster;
+    const size_t wb = nlb * 512 * sizeof(float);
+    const size_t pb = nlb * 512 * dims * sizeof(float);
+    slice_in_smem = (wb + pb <= kSmemBudget);
+    bytes = wb + (slice_in_smem ? pb : 0);
 }
 
 }  // namespace
@@ -427,18 +494,27 @@ int PoseMode::init() {
     VB_CUDA(cudaMalloc((void**)&d_result, sizeof(MeanshiftResult)));
     VB_CUDA(cudaMallocHost((void**)&h_result, sizeof(MeanshiftResult)));
     VB_CUDA(cudaMalloc((void**)&d_partials, (size_t)64 * kMaxTreeBlocks * sizeof(float)));
-    VB_CUDA(cudaMalloc((void**)&d_rg_sums, 256));
+    VB_CUDA(cudaMalloc((void**)&d_rg_sums, 256 + kCluster * sizeof(int)));
     VB_CUDA(cudaMallocHost((void**)&h_rg_sums, 256));
     VB_CUDA(cudaFuncSetAttribute(k_meanshift, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     VB_CUDA(cudaFuncSetAttribute(k_robust_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     return 0;
 }
 
-static int ensure_w_scratch(PoseMode& M, int N) {
-    if ((size_t)N > M.rg_capacity) {
-        if (M.d_rg_scratch) cudaFree(M.d_rg_scratch);
-        VB_CUDA(cudaMalloc((void**)&M.d_rg_scratch, (size_t)N * sizeof(float)));
-        M.rg_capacity = N;
+static int run_meanshift(PoseMode& M, MeanshiftArgs& A, int n_plan, float* h_io_mean, float* h_o_confidence,
+                         int* used_iters) {
+    if (n_plan > 512 * 512) return (int)cudaErrorInvalidValue;
+    size_t smem_bytes;
+    smem_plan(n_plan, A.dims, A.slice_in_smem, smem_bytes);
+    A.src.cta_counts = (int*)((char*)M.d_rg_sums + 256);
+    k_meanshift<<<kCluster, kThreads, smem_bytes, M.stream>>>(A, M.d_partials, M.d_result);
+    VB_RETURN_IF_CUDA_ERROR();
+    VB_CUDA(cudaMemcpyAsync(M.h_result, M.d_result, sizeof(MeanshiftResult), cudaMemcpyDeviceToHost, M.stream));
+    VB_CUDA(cudaStreamSynchronize(M.stream));
+    if (!A.trial_only && M.h_result->used_iters > 0) {
+        if (h_o_confidence) *h_o_confidence = M.h_result->confidence;
+        if (used_iters) *used_iters = M.h_result->used_iters;
+        for (int d = 0; d < A.dims; d++) h_io_mean[d] = M.h_result->mean[d];
     }
     return 0;
 }
@@ -453,8 +529,9 @@ int PoseMode::meanshift(const float* d_space, const float* h_space_for_init, con
     MeanshiftArgs A;
     memset(&A, 0, sizeof(A));
     for (int d = 0; d < dims; d++) A.io_mean[d] = h_io_mean[d];
-    A.n_host = n_host, A.dims = dims, A.kernel_var = kernel_var, A.epsilon = epsilon, A.max_iters = max_iters;
+    A.dims = dims, A.kernel_var = kernel_var, A.epsilon = epsilon, A.max_iters = max_iters;
     A.center_idx = -1, A.trial_only = 0;
+    A.src.space = d_space, A.src.d_n = d_n, A.src.n_host = n_host;
 
     int N = n_host;
     if (!use_external_init_mean) {
@@ -465,22 +542,14 @@ int PoseMode::meanshift(const float* d_space, const float* h_space_for_init, con
             VB_CUDA(cudaStreamSynchronize(stream));
             N = h_result->n;
         }
-        if (N > 512 * 512) return (int)cudaErrorInvalidValue;
-        if (int e = ensure_w_scratch(*this, N)) return e;
-        size_t smem_bytes;
-        smem_plan(N, dims, A.pool_in_smem, A.w_in_smem, smem_bytes);
         float best_conf = 0;
         int best_idx = -1;
         for (int trial = 0; trial < max_init_trials; trial++) {
             const int idx_rand = (rand() % N);
             MeanshiftArgs T = A;
-            T.center_idx = idx_rand, T.trial_only = 1, T.n_host = N;
-            T.pool_in_smem = 0;  // a single pass does not amortise staging the pool
-            k_meanshift<<<1, kThreads, T.w_in_smem ? (size_t)((N + 31) / 32 * 32) * sizeof(float) : 0, stream>>>(
-                d_space, nullptr, T, d_partials, d_rg_scratch, d_result);
-            VB_RETURN_IF_CUDA_ERROR();
-            VB_CUDA(cudaMemcpyAsync(h_result, d_result, sizeof(MeanshiftResult), cudaMemcpyDeviceToHost, stream));
-            VB_CUDA(cudaStreamSynchronize(stream));
+            T.center_idx = idx_rand, T.trial_only = 1;
+            T.src.d_n = nullptr, T.src.n_host = N;
+            if (int e = run_meanshift(*this, T, N, nullptr, nullptr, nullptr)) return e;
             if (h_result->weight_sum > best_conf) {
                 best_conf = h_result->weight_sum;
                 best_idx = idx_rand;
@@ -488,31 +557,11 @@ int PoseMode::meanshift(const float* d_space, const float* h_space_for_init, con
             if (best_conf > good_init_confidence * N) break;
         }
         A.center_idx = best_idx < 0 ? 0 : best_idx;
-        A.n_host = N;
+        A.src.d_n = nullptr, A.src.n_host = N;
         d_n = nullptr;
-    } else if (!d_n && N > 512 * 512) {
-        return (int)cudaErrorInvalidValue;
     }
-
-    // when N lives on the device the shared-memory plan is made for the capacity of the pool
-    const int n_plan = d_n ? n_capacity : N;
-    if (n_plan > 512 * 512) return (int)cudaErrorInvalidValue;
-    if (int e = ensure_w_scratch(*this, n_plan)) return e;
-    size_t smem_bytes;
-    smem_plan(n_plan, dims, A.pool_in_smem, A.w_in_smem, smem_bytes);
-    // layout inside the kernel is derived from the actual N, which is <= n_plan: always fits
-
     if (used_iters) *used_iters = 0;
-    k_meanshift<<<1, kThreads, smem_bytes, stream>>>(d_space, d_n, A, d_partials, d_rg_scratch, d_result);
-    VB_RETURN_IF_CUDA_ERROR();
-    VB_CUDA(cudaMemcpyAsync(h_result, d_result, sizeof(MeanshiftResult), cudaMemcpyDeviceToHost, stream));
-    VB_CUDA(cudaStreamSynchronize(stream));
-    if (h_result->used_iters > 0) {
-        if (h_o_confidence) *h_o_confidence = h_result->confidence;
-        if (used_iters) *used_iters = h_result->used_iters;
-        for (int d = 0; d < dims; d++) h_io_mean[d] = h_result->mean[d];
-    }
-    return 0;
+    return run_meanshift(*this, A, d_n ? n_capacity : N, h_io_mean, h_o_confidence, used_iters);
 }
 
 int PoseMode::meanshift_from_hypotheses(const float* d_rvecs, const float* d_tvecs, int n_poses, float rvec_scale,
@@ -522,25 +571,12 @@ int PoseMode::meanshift_from_hypotheses(const float* d_rvecs, const float* d_tve
     MeanshiftArgs A;
     memset(&A, 0, sizeof(A));
     for (int d = 0; d < dims; d++) A.io_mean[d] = h_io_mean[d];
-    A.n_host = 0, A.dims = dims, A.kernel_var = kernel_var, A.epsilon = epsilon, A.max_iters = max_iters;
+    A.dims = dims, A.kernel_var = kernel_var, A.epsilon = epsilon, A.max_iters = max_iters;
     A.center_idx = -1, A.trial_only = 0;
-    A.rvecs = d_rvecs, A.tvecs = d_tvecs, A.n_poses = n_poses, A.rvec_scale = rvec_scale;
-    A.pool_out = d_pool, A.used_out = d_used;
-    if (n_poses > 512 * 512) return (int)cudaErrorInvalidValue;
-    if (int e = ensure_w_scratch(*this, n_poses)) return e;
-    size_t smem_bytes;
-    smem_plan(n_poses, dims, A.pool_in_smem, A.w_in_smem, smem_bytes);
+    A.src.rvecs = d_rvecs, A.src.tvecs = d_tvecs, A.src.n_poses = n_poses, A.src.rvec_scale = rvec_scale;
+    A.src.pool_out = d_pool, A.src.used_out = d_used;
     if (used_iters) *used_iters = 0;
-    k_meanshift<<<1, kThreads, smem_bytes, stream>>>(nullptr, nullptr, A, d_partials, d_rg_scratch, d_result);
-    VB_RETURN_IF_CUDA_ERROR();
-    VB_CUDA(cudaMemcpyAsync(h_result, d_result, sizeof(MeanshiftResult), cudaMemcpyDeviceToHost, stream));
-    VB_CUDA(cudaStreamSynchronize(stream));
-    if (h_result->used_iters > 0) {
-        if (h_o_confidence) *h_o_confidence = h_result->confidence;
-        if (used_iters) *used_iters = h_result->used_iters;
-        for (int d = 0; d < dims; d++) h_io_mean[d] = h_result->mean[d];
-    }
-    return 0;
+    return run_meanshift(*this, A, n_poses, h_io_mean, h_o_confidence, used_iters);
 }
 
 int PoseMode::fit_robust_gaussian(const float* d_space, int N, int dims, float scale, float* h_io_mean,
@@ -549,21 +585,20 @@ int PoseMode::fit_robust_gaussian(const float* d_space, int N, int dims, float s
     if (int e = init()) return e;
     if (dims > kRobustMaxDims) throw;  // reference: fit_robust_gaussian.cu:107-108
     if (N > 512 * 512 || N <= 0) return (int)cudaErrorInvalidValue;
-    if (int e = ensure_w_scratch(*this, N)) return e;
     RobustArgs A;
     memset(&A, 0, sizeof(A));
     for (int d = 0; d < dims; d++) A.mean[d] = h_io_mean[d];
     for (int d1 = 0; d1 < dims; d1++)
         for (int d2 = 0; d2 <= d1; d2++) A.covar[(d1 * d1 + d1) / 2 + d2] = h_io_covar[d1 * dims + d2];
     A.trunc_sigma = trunc_sigma, A.scale = scale, A.covar_reg_lambda = covar_reg_lambda, A.epsilon = epsilon;
-    A.N = N, A.dims = dims, A.max_iters = max_iters;
+    A.N = N, A.dims = dims, A.max_iters = max_iters, A.space = d_space;
     size_t smem_bytes;
-    smem_plan(N, dims, A.pool_in_smem, A.w_in_smem, smem_bytes);
+    smem_plan(N, dims, A.slice_in_smem, smem_bytes);
     if (used_iters) *used_iters = 0;
 
     RobustResult* d_res = (RobustResult*)d_rg_sums;
     RobustResult* h_res = (RobustResult*)h_rg_sums;
-    k_robust_fit<<<1, kThreads, smem_bytes, stream>>>(d_space, A, d_partials, d_rg_scratch, d_res);
+    k_robust_fit<<<kCluster, kThreads, smem_bytes, stream>>>(A, d_partials, d_res);
     VB_RETURN_IF_CUDA_ERROR();
     VB_CUDA(cudaMemcpyAsync(h_res, d_res, sizeof(RobustResult), cudaMemcpyDeviceToHost, stream));
     VB_CUDA(cudaStreamSynchronize(stream));
