@@ -18,7 +18,7 @@ build/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(LIB): $(OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart
+	$(NVCC) $(ARCH) -shared -Xlinker -Bsymbolic -o $@ $^ -lcudart
 
 oracle:
 	$(MAKE) -C oracle all

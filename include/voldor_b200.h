@@ -72,6 +72,11 @@ int vb_py_voldor_wrapper(const float* flows, const float* disparity, const float
  * series starts from identical state. */
 int vb_set_bootstrap_override(int valid, const float* R9, const float* t3, const float* depth, int w, int h);
 
+/* The monocular bootstrap itself (host code, no GPU needed): relative pose of the first frame pair from one dense
+ * flow map (w*h*2 floats) by an LMedS essential-matrix fit, then the closed-form depth map.  Replaces the OpenCV
+ * calls of voldor/geometry.cpp:288-332 and :267-285.  R9 row-major, |t| = 1.  Returns 0, or 1 if degenerate. */
+int vb_bootstrap_from_flow(const float* flow, int w, int h, const float* K9, float* R9, float* t3, float* depth);
+
 /* Same window call, also reporting the number of EM iterations executed (VOLDOR::solve's return value,
  * voldor/voldor.cpp:148) and per-stage device/host time in ms: stats[0]=total, [1]=cameras, [2]=depth, [3]=io. */
 int vb_py_voldor_wrapper_ex(const float* flows, const float* disparity, const float* disparity_pconf,

@@ -59,3 +59,13 @@ def test_python_binding_fails_loudly_without_library(tmp_path, monkeypatch):
     monkeypatch.setattr(pv, "_LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(ImportError):
         pv.load_library()
+
+
+def test_library_binds_its_own_symbols():
+    """The library exports the reference's mangled names; -Bsymbolic keeps its internal calls bound to itself when
+    a second library with the same names (the reference build, oracle/_ref) lives in the same process."""
+    import subprocess
+    dyn = subprocess.run(["readelf", "-d", ffi.OURS], capture_output=True, text=True).stdout
+    assert "SYMBOLIC" in dyn
+    if os.path.exists(ffi.REF):
+        assert "SYMBOLIC" in subprocess.run(["readelf", "-d", ffi.REF], capture_output=True, text=True).stdout

@@ -100,3 +100,24 @@ def test_disparity_window_bit_exact():
     mine = voldor_b200.voldor_ex(*args, **kw)
     assert ref["n_registered"] > 0
     _compare("window disparity 207x62x3 resident-vs-ref", mine, ref)
+
+
+def test_mono_window_self_bootstrap_converges():
+    """no override: the product's own essential-matrix bootstrap (reference geometry.cpp:267-332, OpenCV there)
+    followed by the EM; functional check against the synthetic ground truth (poses up to the world scale)."""
+    w, h, N = 320, 240, 5
+    win = synth.make_window(w, h, N, seed=21)
+    voldor_b200.set_bootstrap_override()
+    r = voldor_b200.voldor(win["flows"], win["fx"], win["fy"], win["cx"], win["cy"],
+                           config="--silent --max_iters 12 --no_trunc_iters 1000")
+    assert r["n_registered"] == N
+    t_gt = win["ts"].astype(np.float64)
+    scale = N / np.linalg.norm(t_gt, axis=1).sum()  # voldor.cpp:309-317 world-scale normalisation
+    for i in range(N):
+        R = synth.rodrigues(r["poses"][i, :3])
+        assert np.abs(R - win["Rs"][i]).max() < 3e-3, i
+        assert np.linalg.norm(r["poses"][i, 3:] - t_gt[i] * scale) < 0.05, (i, r["poses"][i, 3:], t_gt[i] * scale)
+    d_gt = win["depth_gt"] * scale
+    rigid = r["depth_conf"] > 0.5
+    assert rigid.mean() > 0.5
+    assert np.median(np.abs(r["depth"][rigid] - d_gt[rigid]) / d_gt[rigid]) < 0.03

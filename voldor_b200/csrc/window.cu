@@ -464,8 +464,13 @@ struct Window {
             return 0;
         }
         // essential-matrix bootstrap + closed-form depth on the host (reference geometry.cpp:267-332)
-        std::vector<float> depth((size_t)w * h);
-        if (!boot::bootstrap_from_flow(flows_pt, w, h, K, cams[0].R, cams[0].t, depth.data())) return -1;
+        // flows_pt may be a host or a device pointer; the estimator runs on the host
+        std::vector<float> depth((size_t)w * h), flow0((size_t)w * h * 2);
+        VB_CUDA(cudaMemcpy(flow0.data(), flows_pt, flow0.size() * sizeof(float), cudaMemcpyDefault));
+        if (!boot::bootstrap_from_flow(flow0.data(), w, h, K, cams[0].R, cams[0].t, depth.data())) {
+            fprintf(stderr, "voldor_b200: monocular bootstrap failed (degenerate flow)\n");
+            return -1;
+        }
         VB_CUDA(E.depth.upload_layer(depth.data(), 0, s));
         VB_CUDA(cudaStreamSynchronize(s));
         return 0;
@@ -594,6 +599,10 @@ VB_EXPORT int vb_py_voldor_wrapper_ex(const float* flows, const float* disparity
     return vb::run_window(flows, disparity, disparity_pconf, depth_priors, depth_prior_poses, depth_prior_pconfs, fx, fy,
                           cx, cy, basefocal, N, N_dp, w, h, config, n_registered, poses, poses_covar, depth, depth_conf,
                           iters_run, stats);
+}
+
+VB_EXPORT int vb_bootstrap_from_flow(const float* flow, int w, int h, const float* K9, float* R9, float* t3, float* depth) {
+    return vb::boot::bootstrap_from_flow(flow, w, h, K9, R9, t3, depth) ? 0 : 1;
 }
 
 VB_EXPORT int vb_set_bootstrap_override(int valid, const float* R9, const float* t3, const float* depth, int w, int h) {

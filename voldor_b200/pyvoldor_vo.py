@@ -25,7 +25,7 @@ def load_library():
         raise ImportError(
             f"{_LIB_PATH} is missing: build it with `make lib` (or __graft_entry__.build()); "
             "voldor_b200 has no CPU fallback")
-    lib = C.CDLL(_LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(_LIB_PATH, mode=C.RTLD_LOCAL)
     lib.vb_py_voldor_wrapper_ex.restype = C.c_int
     lib.vb_py_voldor_wrapper_ex.argtypes = [FP] * 6 + [C.c_float] * 5 + [C.c_int] * 4 + [C.c_char_p] + \
         [C.POINTER(C.c_int)] + [FP] * 4 + [C.POINTER(C.c_int), FP]
