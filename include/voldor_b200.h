@@ -92,6 +92,14 @@ int vb_set_device(int device);
  * reporting.  Enabling it adds one event synchronisation per launch, so it is off by default. */
 void vb_profile_enable(int on);
 void vb_profile_get(double* search_ms, long long* search_launches);
+/* Counters of the on-device fixed-point loops since the last vb_profile_enable():
+ * out5 = { mean-shift runs, their iterations, start-sample trials, robust-fit runs, their iterations }. */
+void vb_profile_counters(long long* out5);
+
+/* Test hook for the speculative use of the libc rand() stream by the fused mean-shift start-sample selection
+ * (csrc/libc_rand.h): snapshot, draw `draw` numbers, rewind, draw `keep`.  Afterwards the process-wide stream must
+ * be exactly `keep` draws past where it was.  Returns 0, or 1 if the state array could not be captured. */
+int vb_debug_rand_speculate(int draw, int keep);
 
 /* Library self-description: returns a static string "voldor_b200 <version> sm_100a". */
 const char* vb_version(void);

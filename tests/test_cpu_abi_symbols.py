@@ -69,3 +69,21 @@ def test_library_binds_its_own_symbols():
     assert "SYMBOLIC" in dyn
     if os.path.exists(ffi.REF):
         assert "SYMBOLIC" in subprocess.run(["readelf", "-d", ffi.REF], capture_output=True, text=True).stdout
+
+
+def test_libc_rand_speculation_is_invisible():
+    """fused mean-shift start-sample selection (csrc/libc_rand.h): after snapshot / 20 draws / rewind / k draws the
+    process-wide rand() stream is exactly k draws further — the consumption the reference's loop would show."""
+    lib = C.CDLL(ffi.OURS)
+    libc = C.CDLL(None)
+    for seed, keep in ((5, 3), (77, 0), (123, 20)):
+        libc.srand(seed)
+        want = [libc.rand() for _ in range(keep + 4)]
+        libc.srand(seed)
+        assert lib.vb_debug_rand_speculate(20, keep) == 0
+        got = [libc.rand() for _ in range(4)]
+        assert got == want[keep:], (seed, keep)
+    # and without any srand: the stream simply continues
+    a = libc.rand()
+    assert lib.vb_debug_rand_speculate(7, 0) == 0
+    libc.srand(1)

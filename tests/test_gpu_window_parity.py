@@ -121,3 +121,35 @@ def test_mono_window_self_bootstrap_converges():
     rigid = r["depth_conf"] > 0.5
     assert rigid.mean() > 0.5
     assert np.median(np.abs(r["depth"][rigid] - d_gt[rigid]) / d_gt[rigid]) < 0.03
+
+
+@pytest.mark.parametrize("name,w,h,N,iters,poses,kind", [
+    ("C2", 640, 480, 8, 4, 8192, "mono"),
+    ("C3", 1242, 375, 6, 3, 8192, "stereo"),
+    ("C5", 1280, 960, 12, 2, 4096, "prior"),
+])
+def test_baseline_config_shapes_bit_exact(name, w, h, N, iters, poses, kind):
+    """BASELINE.json configs[1], [2], [4] at their full image size / window length / hypothesis count (iteration
+    count reduced so the reference kernels finish in seconds); resident pipeline vs reference kernels."""
+    win = synth.make_window(w, h, N, seed=41)
+    cfg = f"--silent --max_iters {iters} --no_trunc_iters 1000 --n_poses_to_sample {poses}"
+    args = (win["flows"], win["fx"], win["fy"], win["cx"], win["cy"])
+    kw, boot = dict(config=cfg), None
+    if kind == "mono":
+        boot = (win["Rs"][0], win["ts"][0], synth.noisy_depth(win, 0.05))
+    elif kind == "stereo":
+        basefocal = float(0.54 * win["fx"])
+        rng = np.random.default_rng(3)
+        disp = (basefocal / win["depth_gt"] * (1 + rng.normal(0, 0.02, (h, w)))).astype(np.float32)
+        kw.update(basefocal=basefocal, disparity=disp)
+    else:
+        kw.update(depth_priors=synth.noisy_depth(win, 0.01)[None], depth_prior_poses=np.zeros((1, 6), np.float32))
+    ffi.libc_srand(9)
+    ref = oracle_host.run_window("ref", *args, boot=boot, **kw)
+    if boot:
+        voldor_b200.set_bootstrap_override(*boot)
+    ffi.libc_srand(9)
+    mine = voldor_b200.voldor_ex(*args, **kw)
+    voldor_b200.set_bootstrap_override()
+    assert ref["n_registered"] == N
+    _compare(f"window {name} {w}x{h}x{N} resident-vs-ref", mine, ref)

@@ -24,3 +24,8 @@ cfg = f"--silent --max_iters {a.iters} --no_trunc_iters 1000 --n_poses_to_sample
 for _ in range(a.windows):
     r = voldor_b200.voldor_ex(win["flows"], win["fx"], win["fy"], win["cx"], win["cy"], config=cfg)
 print("n_registered", r["n_registered"], "iters", r["iters"], "stats_ms", r["stats_ms"])
+import ctypes as C  # noqa: E402
+from voldor_b200.pyvoldor_vo import load_library  # noqa: E402
+cnt = (C.c_longlong * 5)()
+load_library().vb_profile_counters(cnt)
+print("meanshift runs/iters/trials, robust runs/iters (all windows):", list(cnt))

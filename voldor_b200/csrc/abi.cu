@@ -6,6 +6,7 @@
 #include "../../include/gpu_kernels.h"
 #include "../../include/voldor_b200.h"
 #include "depth_em.cuh"
+#include "libc_rand.h"
 #include "pose_mode.cuh"
 #include "pose_sampler.cuh"
 #include <mutex>
@@ -249,11 +250,25 @@ DLL_EXPORT void vb_profile_enable(int on) {
     vb::KernelProfile& p = vb::kernel_profile();
     p.enabled = on != 0;
     p.search_ms = 0, p.search_launches = 0;
+    p.meanshift_runs = p.meanshift_iters = p.meanshift_trials = p.robust_runs = p.robust_iters = 0;
+}
+DLL_EXPORT void vb_profile_counters(long long* out5) {
+    vb::KernelProfile& p = vb::kernel_profile();
+    out5[0] = p.meanshift_runs, out5[1] = p.meanshift_iters, out5[2] = p.meanshift_trials;
+    out5[3] = p.robust_runs, out5[4] = p.robust_iters;
 }
 DLL_EXPORT void vb_profile_get(double* search_ms, long long* search_launches) {
     vb::KernelProfile& p = vb::kernel_profile();
     if (search_ms) *search_ms = p.search_ms;
     if (search_launches) *search_launches = p.search_launches;
+}
+DLL_EXPORT int vb_debug_rand_speculate(int draw, int keep) {
+    vb::LibcRandSnapshot snap;
+    if (!snap.take()) return 1;
+    for (int i = 0; i < draw; i++) (void)rand();
+    snap.rewind();
+    for (int i = 0; i < keep; i++) (void)rand();
+    return 0;
 }
 DLL_EXPORT const char* vb_version(void) { return "voldor_b200 0.1 sm_100a"; }
 

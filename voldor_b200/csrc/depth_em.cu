@@ -14,6 +14,7 @@
 // Candidate costs use explicitly rounded FP32 arithmetic in the reference's evaluation order
 // (residual_model.cuh) because the argmin over candidates must reproduce the reference's decisions.
 #include "depth_em.cuh"
+#include <cstdlib>
 #include "residual_model.cuh"
 #include "geometry.cuh"
 #include <cmath>
@@ -687,7 +688,12 @@ int DepthEM::run(int N, int N_dp, const DepthHyper& hp, bool update_rigidness_on
             if (!prof.ev0) cudaEventCreate(&prof.ev0), cudaEventCreate(&prof.ev1);
             cudaEventRecord(prof.ev0, s);
         }
-        k_cost_and_random_search<<<pg, pb, 0, s>>>(A, cam, pcam, hp.n_rand_samples);
+        {
+            // block height of the search kernel: tunable for tail balance (148 SMs x resident blocks vs grid size)
+            static const int by = [] { const char* e = getenv("VB_SEARCH_BLOCK_Y"); return e ? atoi(e) : 8; }();
+            const dim3 sb(32, by), sg(VB_DIV_CEIL(w, 32), VB_DIV_CEIL(h, by));
+            k_cost_and_random_search<<<sg, sb, 0, s>>>(A, cam, pcam, hp.n_rand_samples);
+        }
         if (prof.enabled) {
             // timing one kernel needs a sync; only done when profiling is switched on
             cudaEventRecord(prof.ev1, s);

@@ -64,6 +64,9 @@ struct KernelProfile {
     double search_ms = 0;      // accumulated duration of k_cost_and_random_search
     long long search_launches = 0;
     long long launches = 0;    // all kernel launches issued by the depth step / pose stages since reset
+    // fixed-point loops of the pose-mode kernels (always counted; host-side bookkeeping only)
+    long long meanshift_runs = 0, meanshift_iters = 0, meanshift_trials = 0;
+    long long robust_runs = 0, robust_iters = 0;
 };
 KernelProfile& kernel_profile();
 

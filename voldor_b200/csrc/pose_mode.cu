@@ -3,14 +3,17 @@
 // Both run as ONE launch of ONE thread-block cluster (8 CTAs x 512 threads, distributed over 8 SMs): the pose
 // pool (<= 8192 x 6 floats) is split by 512-element tree blocks over the CTAs and staged in their shared memory;
 // every iteration of the fixed-point loop runs on the device — weights, the reference-ordered tree sums
-// (tree_sum.cuh; level-1 partials are exchanged through L2 with one hardware cluster barrier per iteration,
-// double buffered), the host-side arithmetic of the reference's loop (mean update / displacement test; 6x6 FP64
-// LU, inverse and shrinkage for the robust fit — evaluated redundantly and identically by every CTA) and the
-// convergence test.  One launch replaces the reference's up to 100 x (kernel + 2..3 multi-pass reductions +
+// (tree_sum.cuh; every CTA stores its level-1 partials straight into the partial table of all 8 CTAs through
+// distributed shared memory, one hardware cluster barrier per iteration, double buffered; pools beyond 32768
+// elements exchange through L2 instead), the host-side arithmetic of the reference's loop (mean update /
+// displacement test; 6x6 FP64 LU, inverse and shrinkage for the robust fit — evaluated redundantly and
+// identically by every CTA) and the convergence test.  One launch replaces the reference's up to 100 x (kernel + 2..3 multi-pass reductions +
 // 2..4 blocking copies) per call.
 #include "pose_mode.cuh"
+#include "depth_em.cuh"
 #include "residual_model.cuh"
 #include "tree_sum.cuh"
+#include "libc_rand.h"
 #include <cmath>
 #include <cooperative_groups.h>
 #include <cstdlib>
@@ -25,6 +28,9 @@ constexpr int kCluster = 8;
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxTreeBlocks = 512;  // pool size limit 512*512 (two tree levels)
+constexpr int kDsmemBlocks = 64;     // pools up to 64*512 elements exchange partial sums through DSMEM
+constexpr int kMaxTrialBatch = 32;   // start-sample trials evaluated inside one launch
+constexpr int kMeanshiftQ = kMaxTrialBatch > kMeanshiftMaxDims + 1 ? kMaxTrialBatch : kMeanshiftMaxDims + 1;
 constexpr size_t kSmemBudget = 200 * 1024;
 
 struct PoolSource {
@@ -49,6 +55,10 @@ struct MeanshiftArgs {
     float kernel_var, epsilon;
     int max_iters;
     int slice_in_smem;
+    // start-sample selection fused into the launch (reference host loop meanshift.cu:73-97): n_trials > 0
+    int n_trials;
+    int trial_idx[kMaxTrialBatch];
+    float good_init_confidence;
     PoolSource src;
 };
 
@@ -131,9 +141,29 @@ __device__ void stage_slice(Slice& S, float* smem_pool, bool in_smem) {
     S.local = smem_pool;
 }
 
+// Where the level-1 partial sums of one iteration live: a [Q][stride] table in the shared memory of every CTA
+// (DSMEM exchange) or in global memory.
+struct Exchange {
+    float* table;
+    int stride;
+    bool dsmem;
+};
+__device__ __forceinline__ Exchange exchange_for(int iter, int NB, float* s_table, int q_max, float* partials_g) {
+    Exchange X;
+    X.dsmem = NB <= kDsmemBlocks;
+    X.stride = X.dsmem ? kDsmemBlocks : kMaxTreeBlocks;
+    X.table = (X.dsmem ? s_table : partials_g) + (size_t)(iter & 1) * q_max * X.stride;
+    return X;
+}
+__device__ __forceinline__ void exchange_sync(const Exchange& X, cg::cluster_group& cluster) {
+    if (!X.dsmem) __threadfence();
+    cluster.sync();  // barrier.cluster arrive.release / wait.acquire: remote shared-memory stores are visible after it
+}
+
 // level 1: one warp per (local tree block, quantity); level 2: one warp per quantity (every CTA, redundantly)
 template <class Val>
-__device__ __forceinline__ void tree_level1(const Slice& S, int Q, float* partials, Val val) {
+__device__ __forceinline__ void tree_level1(const Slice& S, int Q, const Exchange& X, cg::cluster_group& cluster,
+                                            Val val) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int task = warp; task < S.nlb * Q; task += kWarps) {
         const int q = task / S.nlb, lb = task % S.nlb;
@@ -141,17 +171,20 @@ __device__ __forceinline__ void tree_level1(const Slice& S, int Q, float* partia
         if (b >= S.NB) continue;
         const int count = min(512, S.N - b * 512);
         float v = tree_sum_512([&](int i) { return val(q, lb * 512 + i); }, count, lane);
-        if (lane == 0) {
-            if (S.N == 1) v = val(q, 0);  // the reference launches no reduction at all for a single element
-            partials[q * kMaxTreeBlocks + b] = v;
+        if (lane == 0 && S.N == 1) v = val(q, 0);  // the reference launches no reduction at all for a single element
+        float* dst = X.table + q * X.stride + b;
+        if (X.dsmem) {
+            v = __shfl_sync(0xffffffffu, v, 0);
+            if (lane < kCluster) *cluster.map_shared_rank(dst, lane) = v;
+        } else if (lane == 0) {
+            *dst = v;
         }
     }
 }
-__device__ __forceinline__ void tree_level2(int NB, int Q, const float* partials, float* sums) {
+__device__ __forceinline__ void tree_level2(int NB, int Q, const Exchange& X, float* sums) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const volatile float* pv = partials;
     for (int q = warp; q < Q; q += kWarps) {
-        const volatile float* p = pv + q * kMaxTreeBlocks;
+        const volatile float* p = X.table + q * X.stride;
         const float v = (NB == 1) ? p[0] : tree_sum_512([&](int i) { return (float)p[i]; }, NB, lane);
         if (lane == 0) sums[q] = v;
     }
@@ -165,12 +198,18 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     extern __shared__ float smem[];
     __shared__ float c_mean[kMeanshiftMaxDims];
     __shared__ float io_mean[kMeanshiftMaxDims];
-    __shared__ float sums[kMeanshiftMaxDims + 1];
+    __shared__ float sums[kMeanshiftQ];
+    __shared__ float s_part[2 * kMeanshiftQ * kDsmemBlocks];
+    __shared__ float s_trial[kMaxTrialBatch * kMeanshiftMaxDims];
+    __shared__ int s_center_idx, s_trials_used;
     __shared__ int done;
+    __shared__ int s_used_iters;
+    __shared__ float s_confidence, s_wsum;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int dims = A.dims;
     const int Q = A.trial_only ? 1 : dims + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     int N;
     const float* space_g = A.src.space;
@@ -179,6 +218,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
         space_g = A.src.pool_out;
     } else {
         N = A.src.d_n ? *A.src.d_n : A.src.n_host;
+        cluster.sync();  // every CTA of the cluster is resident before anyone stores into its shared memory
     }
     if (N <= 0) {
         if (rank == 0 && threadIdx.x == 0) out->used_iters = 0, out->n = N, out->weight_sum = 0.f, out->confidence = 0.f;
@@ -190,22 +230,55 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     if (S.nlb < 0) S.nlb = 0;
     float* wv = smem;  // weights of the local slice
     stage_slice(S, smem + (size_t)S.nlb * 512, A.slice_in_smem != 0);
+    const float two_var = f_add(A.kernel_var, A.kernel_var);  // 2*kernel_var
+    if (threadIdx.x == 0) s_center_idx = A.center_idx, s_trials_used = 0;
+    if (A.n_trials > 0) {
+        // weight sum around every trial sample, then the reference's selection loop
+        const int T = A.n_trials;
+        for (int k = threadIdx.x; k < T * dims; k += kThreads)
+            s_trial[k] = ((const volatile float*)space_g)[(size_t)A.trial_idx[k / dims] * dims + (k % dims)];
+        __syncthreads();
+        const Exchange X = exchange_for(1, S.NB, s_part, kMeanshiftQ, partials_g);
+        tree_level1(S, T, X, cluster, [&](int q, int li) {
+            float l2 = 0.f;
+            for (int d = 0; d < dims; d++) {
+                const float diff = f_sub(S.x(li, d), s_trial[q * dims + d]);
+                l2 = f_fma(diff, diff, l2);
+            }
+            return expf(f_div(-l2, two_var));
+        });
+        exchange_sync(X, cluster);
+        tree_level2(S.NB, T, X, sums);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float best_conf = 0.f;
+            int best_idx = -1, used = T;
+            const float good = f_mul(A.good_init_confidence, (float)N);
+            for (int trial = 0; trial < T; trial++) {
+                if (sums[trial] > best_conf) best_conf = sums[trial], best_idx = A.trial_idx[trial];
+                if (best_conf > good) {
+                    used = trial + 1;
+                    break;
+                }
+            }
+            s_center_idx = best_idx < 0 ? 0 : best_idx;
+            s_trials_used = used;
+        }
+    }
+    __syncthreads();
     if (threadIdx.x < dims) {
         io_mean[threadIdx.x] = A.io_mean[threadIdx.x];
-        c_mean[threadIdx.x] = (A.center_idx >= 0)
-                                  ? ((const volatile float*)space_g)[(size_t)A.center_idx * dims + threadIdx.x]
+        c_mean[threadIdx.x] = (s_center_idx >= 0)
+                                  ? ((const volatile float*)space_g)[(size_t)s_center_idx * dims + threadIdx.x]
                                   : A.io_mean[threadIdx.x];
     }
-    if (threadIdx.x == 0) done = 0;
+    if (threadIdx.x == 0) done = 0, s_used_iters = 0, s_confidence = 0.f, s_wsum = 0.f;
     __syncthreads();
 
-    const float two_var = f_add(A.kernel_var, A.kernel_var);  // 2*kernel_var
     const int n_iters = A.trial_only ? 1 : A.max_iters;
-    int used_iters = 0;
-    float confidence = 0.f, wsum_last = 0.f;
 
     for (int iter = 0; iter < n_iters; iter++) {
-        float* partials = partials_g + (size_t)(iter & 1) * 32 * kMaxTreeBlocks;
+        const Exchange X = exchange_for(iter, S.NB, s_part, kMeanshiftQ, partials_g);
         // weights w_i = exp(-|x_i - mu|^2 / (2 var)) of the local slice
         for (int li = threadIdx.x; li < S.nlb * 512; li += kThreads) {
             float wgt = 0.f;
@@ -220,28 +293,32 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
             wv[li] = wgt;
         }
         __syncthreads();
-        tree_level1(S, Q, partials, [&](int q, int li) { return q == 0 ? wv[li] : f_mul(wv[li], S.x(li, q - 1)); });
-        __threadfence();
-        cluster.sync();
-        tree_level2(S.NB, Q, partials, sums);
+        tree_level1(S, Q, X, cluster, [&](int q, int li) { return q == 0 ? wv[li] : f_mul(wv[li], S.x(li, q - 1)); });
+        exchange_sync(X, cluster);
+        tree_level2(S.NB, Q, X, sums);
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (warp == 0) {
+            // host part of the reference iteration (meanshift.cu:112-133), one lane per dimension
             const float wsum = sums[0];
-            wsum_last = wsum;
-            if (!A.trial_only) {
-                // host part of the reference iteration (meanshift.cu:112-133)
-                float mean_new[kMeanshiftMaxDims];
-                for (int d = 0; d < dims; d++) mean_new[d] = f_div(sums[d + 1], wsum);
-                confidence = f_div(wsum, (float)N);
-                used_iters = iter + 1;
-                float disp = 0.f;
-                for (int d = 0; d < dims; d++) {
-                    const float df = f_sub(io_mean[d], mean_new[d]);
-                    disp = f_add(disp, f_mul(df, df));
+            if (A.trial_only) {
+                if (lane == 0) s_wsum = wsum;
+            } else {
+                float mean_new = 0.f, sq = 0.f;
+                if (lane < dims) {
+                    mean_new = f_div(sums[lane + 1], wsum);
+                    const float df = f_sub(io_mean[lane], mean_new);
+                    sq = f_mul(df, df);
                 }
+                float disp = 0.f;
+                for (int d = 0; d < dims; d++) disp = f_add(disp, __shfl_sync(0xffffffffu, sq, d));
                 disp = __fsqrt_rn(disp);
-                for (int d = 0; d < dims; d++) io_mean[d] = mean_new[d], c_mean[d] = mean_new[d];
-                if (disp < A.epsilon) done = 1;
+                if (lane < dims) io_mean[lane] = mean_new, c_mean[lane] = mean_new;
+                if (lane == 0) {
+                    s_wsum = wsum;
+                    s_confidence = f_div(wsum, (float)N);
+                    s_used_iters = iter + 1;
+                    if (disp < A.epsilon) done = 1;
+                }
             }
         }
         __syncthreads();
@@ -249,9 +326,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     }
     if (rank == 0 && threadIdx.x == 0) {
         for (int d = 0; d < dims; d++) out->mean[d] = io_mean[d];
-        out->confidence = confidence;
-        out->weight_sum = wsum_last;
-        out->used_iters = used_iters;
+        out->confidence = s_confidence;
+        out->weight_sum = s_wsum;
+        out->used_iters = s_used_iters;
+        out->trials_used = s_trials_used;
         out->n = N;
     }
 }
@@ -265,7 +343,7 @@ struct RobustArgs {
     float covar[21];  // lower-triangular packed start covariance
     float trunc_sigma, scale, covar_reg_lambda, epsilon;
     int N, dims, max_iters;
-    int slice_in_smem;
+    int slice_in_smem, centred_in_smem;
     const float* space;
 };
 struct RobustResult {
@@ -288,132 +366,133 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     __shared__ float s_mean[kRobustMaxDims];
     __shared__ float s_cov[21], s_cinv[21];
     __shared__ float sums[28];
-    __shared__ int s_state;  // 0 continue, 1 converged/reliable, 2 unreliable
-    __shared__ float s_weight;
-    // 6x6 FP64 scratch of the covariance step: LU with partial pivoting run by the 36 threads (r,c) of the
-    // augmented matrix [a | b] in shared memory — the same operations on the same elements as the sequential host
-    // code it mirrors (aux shim / cv::Matx66d), only issued in parallel
-    __shared__ double sa[36], sb[36], s_inv[36];
-    __shared__ double s_det;
-    __shared__ int s_piv;
+    __shared__ float s_part[2 * 28 * kDsmemBlocks];
+    __shared__ int s_d1[28], s_d2[28];  // (row, column) of the packed lower-triangular covariance terms
+    __shared__ int s_lu_state;          // 0 ok, 2 unreliable (det <= 0)
+    // 6x6 FP64 scratch of the covariance step: LU with partial pivoting on the augmented matrix [a | b], run by
+    // warp 0 with one lane per column — the same operations on the same elements as the sequential host code it
+    // mirrors (aux shim / cv::Matx66d), only issued in parallel
+    __shared__ double sa[36], sb[36];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int N = A.N, dims = A.dims;
     const int cdims = (dims * dims + dims) / 2;
     const int Q = 1 + dims + cdims;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 
+    cluster.sync();  // every CTA of the cluster is resident before anyone stores into its shared memory
     Slice S;
     S.N = N, S.NB = (N + 511) / 512, S.rank = rank, S.dims = dims, S.global = A.space;
     S.nlb = (S.NB - rank + kCluster - 1) / kCluster;
     if (S.nlb < 0) S.nlb = 0;
+    const int n_local = S.nlb * 512;
     float* wv = smem;
-    stage_slice(S, smem + (size_t)S.nlb * 512, A.slice_in_smem != 0);
-    const int t = threadIdx.x;
+    stage_slice(S, smem + (size_t)n_local, A.slice_in_smem != 0);
+    // centred, scaled coordinates of the local slice (rewritten by every E-step)
+    float* av = A.centred_in_smem ? smem + (size_t)n_local * (1 + (A.slice_in_smem ? dims : 0)) : nullptr;
     if (t == 0) {
         for (int d = 0; d < dims; d++) s_mean[d] = A.mean[d];
         for (int k = 0; k < cdims; k++) s_cov[k] = A.covar[k];
-        s_weight = 0.f;
-        s_state = 0;
+        for (int d1 = 0; d1 < dims; d1++)
+            for (int d2 = 0; d2 <= d1; d2++) s_d1[(d1 * d1 + d1) / 2 + d2] = d1, s_d2[(d1 * d1 + d1) / 2 + d2] = d2;
     }
-    const int mr = t / 6, mc = t % 6;
-    const bool in_mat = t < 36 && mr < dims && mc < dims;
-    if (t < 36) s_inv[t] = 0.0;
     __syncthreads();
 
+    float weight = 0.f;  // sum of weights of the previous E-step (uniform over all threads)
+    int state = 0;       // 0 continue, 1 converged, 2 unreliable (uniform)
     int iter = 0;
     for (iter = 0; iter < A.max_iters; iter++) {
-        float* partials = partials_g + (size_t)(iter & 1) * 32 * kMaxTreeBlocks;
-        if (t == 0) {
+        const Exchange X = exchange_for(iter, S.NB, s_part, 28, partials_g);
+        if (warp == 0) {
             // half -> full (double); shrink towards tr/n * I from the 2nd iteration on
-            for (int d1 = 0; d1 < dims; d1++)
-                for (int d2 = 0; d2 <= d1; d2++) {
-                    sa[d1 * 6 + d2] = (double)s_cov[(d1 * d1 + d1) / 2 + d2];
-                    if (d1 != d2) sa[d2 * 6 + d1] = sa[d1 * 6 + d2];
+            for (int e = lane; e < 36; e += 32) {
+                const int r = e / 6, c = e % 6;
+                if (r < dims && c < dims) {
+                    const int hi = r > c ? r : c, lo = r > c ? c : r;
+                    sa[e] = (double)s_cov[(hi * hi + hi) / 2 + lo];
+                    sb[e] = (r == c) ? 1.0 : 0.0;
                 }
+            }
+            __syncwarp();
             if (iter > 0 && A.covar_reg_lambda > 0) {
                 const double lambda = (double)A.covar_reg_lambda;
                 double tr = 0;
                 for (int i = 0; i < dims; i++) tr = d_add(tr, sa[i * 6 + i]);
                 const double m = d_div(tr, (double)dims);
                 const double lm = d_mul(lambda, m), oml = d_sub(1.0, lambda);
-                for (int i = 0; i < dims; i++)
-                    for (int j = 0; j < dims; j++)
-                        sa[i * 6 + j] = d_add(d_mul(lm, i == j ? 1.0 : 0.0), d_mul(oml, sa[i * 6 + j]));
+                __syncwarp();
+                for (int e = lane; e < 36; e += 32) {
+                    const int r = e / 6, c = e % 6;
+                    if (r < dims && c < dims) sa[e] = d_add(d_mul(lm, r == c ? 1.0 : 0.0), d_mul(oml, sa[e]));
+                }
+                __syncwarp();
             }
             // the regularised covariance is the one reported on convergence (fit_robust_gaussian.cu:203)
-            for (int d1 = 0; d1 < dims; d1++)
-                for (int d2 = 0; d2 <= d1; d2++) s_cov[(d1 * d1 + d1) / 2 + d2] = (float)sa[d1 * 6 + d2];
-            s_det = 1.0;
-        }
-        if (in_mat) sb[t] = (mr == mc) ? 1.0 : 0.0;
-        __syncthreads();
-        bool singular = false;
-        for (int i = 0; i < dims; i++) {
-            if (t == 0) {
+            for (int e = lane; e < 36; e += 32) {
+                const int r = e / 6, c = e % 6;
+                if (r < dims && c <= r) s_cov[(r * r + r) / 2 + c] = (float)sa[e];
+            }
+            __syncwarp();
+            // lanes 0..5 own the columns of a, lanes 6..11 the columns of b
+            const bool is_a = lane < 6 && lane < dims;
+            const bool is_b = lane >= 6 && lane < 12 && lane - 6 < dims;
+            const int col = lane < 6 ? lane : lane - 6;
+            double det = 1.0;
+            bool singular = false;
+            for (int i = 0; i < dims; i++) {
                 int k = i;
                 for (int j = i + 1; j < dims; j++)
                     if (fabs(sa[j * 6 + i]) > fabs(sa[k * 6 + i])) k = j;
-                s_piv = (fabs(sa[k * 6 + i]) < 2.220446049250313e-16 * 100) ? -1 : k;
-            }
-            __syncthreads();
-            const int k = s_piv;
-            if (k < 0) {
-                singular = true;
-                break;
-            }
-            if (k != i) {
-                if (in_mat && mr == i) {
-                    if (mc >= i) {
-                        const double tmp = sa[i * 6 + mc];
-                        sa[i * 6 + mc] = sa[k * 6 + mc];
-                        sa[k * 6 + mc] = tmp;
+                if (fabs(sa[k * 6 + i]) < 2.220446049250313e-16 * 100) {
+                    singular = true;
+                    break;
+                }
+                __syncwarp();
+                if (k != i) {
+                    if ((is_a && col >= i) || is_b) {
+                        double* m = is_a ? sa : sb;
+                        const double tmp = m[i * 6 + col];
+                        m[i * 6 + col] = m[k * 6 + col];
+                        m[k * 6 + col] = tmp;
                     }
-                    const double tmp = sb[i * 6 + mc];
-                    sb[i * 6 + mc] = sb[k * 6 + mc];
-                    sb[k * 6 + mc] = tmp;
+                    det = -det;
+                    __syncwarp();
                 }
-                if (t == 0) s_det = -s_det;
-                __syncthreads();
-            }
-            double na = 0, nb = 0;
-            const bool upd = in_mat && mr > i;
-            if (upd) {
-                const double d = d_div(-1.0, sa[i * 6 + i]);
-                const double alpha = d_mul(sa[mr * 6 + i], d);
-                na = (mc > i) ? d_add(sa[mr * 6 + mc], d_mul(alpha, sa[i * 6 + mc])) : sa[mr * 6 + mc];
-                nb = d_add(sb[mr * 6 + mc], d_mul(alpha, sb[i * 6 + mc]));
-            }
-            __syncthreads();
-            if (upd) sa[mr * 6 + mc] = na, sb[mr * 6 + mc] = nb;
-            if (t == 0) s_det = d_mul(s_det, sa[i * 6 + i]);
-            __syncthreads();
-        }
-        const double det = singular ? 0.0 : s_det;
-        if (det > 0) {  // inverse only written for det > 0 (aux_funs.cpp:104-111)
-            for (int i = dims - 1; i >= 0; i--) {
-                if (t < dims) {
-                    double acc = sb[i * 6 + t];
-                    for (int k = i + 1; k < dims; k++) acc = d_sub(acc, d_mul(sa[i * 6 + k], sb[k * 6 + t]));
-                    sb[i * 6 + t] = d_div(acc, sa[i * 6 + i]);
+                const double piv = sa[i * 6 + i];
+                const double d = d_div(-1.0, piv);
+                for (int r = i + 1; r < dims; r++) {
+                    const double alpha = d_mul(sa[r * 6 + i], d);
+                    if (is_a && col > i) sa[r * 6 + col] = d_add(sa[r * 6 + col], d_mul(alpha, sa[i * 6 + col]));
+                    if (is_b) sb[r * 6 + col] = d_add(sb[r * 6 + col], d_mul(alpha, sb[i * 6 + col]));
                 }
-                __syncthreads();
+                det = d_mul(det, piv);
+                __syncwarp();
             }
-            if (in_mat) s_inv[t] = sb[t];
+            if (singular) det = 0.0;
+            if (det > 0) {  // inverse only written for det > 0 (aux_funs.cpp:104-111)
+                if (is_b) {
+                    for (int i = dims - 1; i >= 0; i--) {
+                        double acc = sb[i * 6 + col];
+                        for (int k = i + 1; k < dims; k++) acc = d_sub(acc, d_mul(sa[i * 6 + k], sb[k * 6 + col]));
+                        sb[i * 6 + col] = d_div(acc, sa[i * 6 + i]);
+                    }
+                }
+                __syncwarp();
+                for (int e = lane; e < 36; e += 32) {
+                    const int r = e / 6, c = e % 6;
+                    if (r < dims && c <= r) s_cinv[(r * r + r) / 2 + c] = (float)sb[e];
+                }
+            }
+            if (lane == 0) s_lu_state = det > 0 ? 0 : 2;
         }
         __syncthreads();
-        if (t == 0) {
-            if (det <= 0) {
-                s_state = 2;
-            } else {
-                for (int d1 = 0; d1 < dims; d1++)
-                    for (int d2 = 0; d2 <= d1; d2++) s_cinv[(d1 * d1 + d1) / 2 + d2] = (float)s_inv[d1 * 6 + d2];
-            }
+        if (s_lu_state == 2) {
+            state = 2;
+            break;
         }
-        __syncthreads();
-        if (s_state == 2) break;
 
         // E-step weights: hard truncation of the Mahalanobis distance (fit_robust_gaussian.cu:67-86)
-        for (int li = t; li < S.nlb * 512; li += kThreads) {
+        for (int li = t; li < n_local; li += kThreads) {
             float wgt = 0.f;
             if (S.gidx(li) < N) {
                 float diff[kRobustMaxDims];
@@ -429,60 +508,65 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
                 }
                 z = __fsqrt_rn(z);
                 wgt = z < A.trunc_sigma ? 1.f : 0.f;
+                if (av)
+                    for (int d = 0; d < dims; d++) av[(size_t)li * dims + d] = diff[d];
             }
             wv[li] = wgt;
         }
         __syncthreads();
         // weighted moments, reference tree order
-        tree_level1(S, Q, partials, [&](int q, int li) {
+        tree_level1(S, Q, X, cluster, [&](int q, int li) {
             const float w = wv[li];
             if (q == 0) return w;
             if (q <= dims) return f_mul(w, f_mul(S.x(li, q - 1), A.scale));
-            int k = q - 1 - dims, d1 = 0;
-            while ((d1 + 1) * (d1 + 2) / 2 <= k) d1++;
-            const int d2 = k - (d1 * d1 + d1) / 2;
-            const float a = f_sub(f_mul(S.x(li, d1), A.scale), s_mean[d1]);
-            const float b = f_sub(f_mul(S.x(li, d2), A.scale), s_mean[d2]);
+            const int d1 = s_d1[q - 1 - dims], d2 = s_d2[q - 1 - dims];
+            const float a = av ? av[(size_t)li * dims + d1] : f_sub(f_mul(S.x(li, d1), A.scale), s_mean[d1]);
+            const float b = av ? av[(size_t)li * dims + d2] : f_sub(f_mul(S.x(li, d2), A.scale), s_mean[d2]);
             return f_mul(f_mul(w, a), b);
         });
-        __threadfence();
-        cluster.sync();
-        tree_level2(S.NB, Q, partials, sums);
+        exchange_sync(X, cluster);
+        tree_level2(S.NB, Q, X, sums);
         __syncthreads();
-        if (t == 0) {
-            // host part of the reference iteration (fit_robust_gaussian.cu:209-246)
-            const float prev_density = f_div(s_weight, (float)N);
+        {
+            // host part of the reference iteration (fit_robust_gaussian.cu:209-246); the decision is evaluated by
+            // every thread, the divisions of the M-step by one thread per moment
+            const float prev_density = f_div(weight, (float)N);
             const float wsum = sums[0];
-            s_weight = wsum;
+            weight = wsum;
             if (!isfinite(wsum)) {
-                s_state = 2;
+                state = 2;
             } else if (fabsf(f_sub(f_div(wsum, (float)N), prev_density)) < A.epsilon) {
-                s_state = 1;  // converged: keep the moments used in this E-step
-            } else {
-                for (int d = 0; d < dims; d++) s_mean[d] = f_div(sums[1 + d], wsum);
-                for (int k = 0; k < cdims; k++) s_cov[k] = f_div(sums[1 + dims + k], wsum);
+                state = 1;  // converged: keep the moments used in this E-step
+            } else if (t < dims) {
+                s_mean[t] = f_div(sums[1 + t], wsum);
+            } else if (t < dims + cdims) {
+                s_cov[t - dims] = f_div(sums[1 + t], wsum);
             }
         }
         __syncthreads();
-        if (s_state != 0) break;
+        if (state != 0) break;
     }
     if (rank == 0 && t == 0) {
-        out->reliable = (s_state != 2);
+        out->reliable = (state != 2);
         out->used_iters = iter;
-        out->density = f_div(s_weight, (float)N);
+        out->density = f_div(weight, (float)N);
         for (int d = 0; d < dims; d++) out->mean[d] = s_mean[d];
         for (int k = 0; k < cdims; k++) out->covar[k] = s_cov[k];
     }
 }
 
 // shared-memory plan for a pool of at most n elements: weights + (if it fits) the slice of every CTA
-void smem_plan(int n, int dims, int& slice_in_smem, size_t& bytes) {
+void smem_plan(int n, int dims, int& slice_in_smem, size_t& bytes, int* centred_in_smem = nullptr) {
     const int NB = (n + 511) / 512;
     const size_t nlb = (size_t)(NB + kCluster - 1) / kCluster;
     const size_t wb = nlb * 512 * sizeof(float);
     const size_t pb = nlb * 512 * dims * sizeof(float);
     slice_in_smem = (wb + pb <= kSmemBudget);
     bytes = wb + (slice_in_smem ? pb : 0);
+    if (centred_in_smem) {
+        *centred_in_smem = (bytes + pb <= kSmemBudget);
+        if (*centred_in_smem) bytes += pb;
+    }
 }
 
 }  // namespace
@@ -511,6 +595,11 @@ static int run_meanshift(PoseMode& M, MeanshiftArgs& A, int n_plan, float* h_io_
     VB_RETURN_IF_CUDA_ERROR();
     VB_CUDA(cudaMemcpyAsync(M.h_result, M.d_result, sizeof(MeanshiftResult), cudaMemcpyDeviceToHost, M.stream));
     VB_CUDA(cudaStreamSynchronize(M.stream));
+    KernelProfile& prof = kernel_profile();
+    if (A.trial_only)
+        prof.meanshift_trials++;
+    else
+        prof.meanshift_runs++, prof.meanshift_iters += M.h_result->used_iters;
     if (!A.trial_only && M.h_result->used_iters > 0) {
         if (h_o_confidence) *h_o_confidence = M.h_result->confidence;
         if (used_iters) *used_iters = M.h_result->used_iters;
@@ -542,13 +631,32 @@ int PoseMode::meanshift(const float* d_space, const float* h_space_for_init, con
             VB_CUDA(cudaStreamSynchronize(stream));
             N = h_result->n;
         }
+        if (N <= 0) return (int)cudaErrorInvalidValue;
+        A.src.d_n = nullptr, A.src.n_host = N;
+        d_n = nullptr;
+        LibcRandSnapshot snap;
+        if (max_init_trials > 0 && max_init_trials <= kMaxTrialBatch && snap.take()) {
+            // all trials + the selection loop + the iteration in one launch; the libc stream is rewound to the
+            // number of draws the reference's early-exit loop would have consumed (libc_rand.h)
+            A.n_trials = max_init_trials;
+            A.good_init_confidence = good_init_confidence;
+            for (int trial = 0; trial < max_init_trials; trial++) A.trial_idx[trial] = rand() % N;
+            if (used_iters) *used_iters = 0;
+            if (int e = run_meanshift(*this, A, N, h_io_mean, h_o_confidence, used_iters)) return e;
+            const int used = h_result->trials_used;
+            kernel_profile().meanshift_trials += used;
+            if (used < max_init_trials) {
+                snap.rewind();
+                for (int trial = 0; trial < used; trial++) (void)rand();
+            }
+            return 0;
+        }
         float best_conf = 0;
         int best_idx = -1;
         for (int trial = 0; trial < max_init_trials; trial++) {
             const int idx_rand = (rand() % N);
             MeanshiftArgs T = A;
             T.center_idx = idx_rand, T.trial_only = 1;
-            T.src.d_n = nullptr, T.src.n_host = N;
             if (int e = run_meanshift(*this, T, N, nullptr, nullptr, nullptr)) return e;
             if (h_result->weight_sum > best_conf) {
                 best_conf = h_result->weight_sum;
@@ -557,8 +665,6 @@ int PoseMode::meanshift(const float* d_space, const float* h_space_for_init, con
             if (best_conf > good_init_confidence * N) break;
         }
         A.center_idx = best_idx < 0 ? 0 : best_idx;
-        A.src.d_n = nullptr, A.src.n_host = N;
-        d_n = nullptr;
     }
     if (used_iters) *used_iters = 0;
     return run_meanshift(*this, A, d_n ? n_capacity : N, h_io_mean, h_o_confidence, used_iters);
@@ -593,7 +699,7 @@ int PoseMode::fit_robust_gaussian(const float* d_space, int N, int dims, float s
     A.trunc_sigma = trunc_sigma, A.scale = scale, A.covar_reg_lambda = covar_reg_lambda, A.epsilon = epsilon;
     A.N = N, A.dims = dims, A.max_iters = max_iters, A.space = d_space;
     size_t smem_bytes;
-    smem_plan(N, dims, A.slice_in_smem, smem_bytes);
+    smem_plan(N, dims, A.slice_in_smem, smem_bytes, &A.centred_in_smem);
     if (used_iters) *used_iters = 0;
 
     RobustResult* d_res = (RobustResult*)d_rg_sums;
@@ -602,6 +708,7 @@ int PoseMode::fit_robust_gaussian(const float* d_space, int N, int dims, float s
     VB_RETURN_IF_CUDA_ERROR();
     VB_CUDA(cudaMemcpyAsync(h_res, d_res, sizeof(RobustResult), cudaMemcpyDeviceToHost, stream));
     VB_CUDA(cudaStreamSynchronize(stream));
+    kernel_profile().robust_runs++, kernel_profile().robust_iters += h_res->used_iters;
 
     if (h_res->reliable) {
         if (h_o_density) *h_o_density = h_res->density;

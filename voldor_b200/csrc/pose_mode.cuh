@@ -1,10 +1,10 @@
 // Mode seeking over the pose-hypothesis pool: Gaussian mean-shift and truncated robust Gaussian fit.
 //
 // Replaces reference gpu-kernels/meanshift.cu:34-150 (host loop of <=100 iterations, each 1 kernel +
-// 2 multi-pass reductions + 2 blocking D2H + 1 cudaMemcpyToSymbol) with ONE persistent single-CTA kernel
-// that runs all iterations on the device, and reference gpu-kernels/fit_robust_gaussian.cu:101-286 with one
-// fused E-step+reduction launch per iteration (the 6x6 FP64 determinant/inverse/shrinkage stays on the
-// host, as in the reference: aux_funs.cpp:101-141).
+// 2 multi-pass reductions + 2 blocking D2H + 1 cudaMemcpyToSymbol, preceded by <=20 start-sample trials of the
+// same shape) and reference gpu-kernels/fit_robust_gaussian.cu:101-286 + aux_funs.cpp:101-141 (host loop with a
+// 6x6 FP64 determinant/inverse/shrinkage per iteration) with ONE launch each of an 8-CTA thread-block cluster
+// that runs the whole fixed-point loop on the device (pose_mode.cu).
 #pragma once
 #include "common.cuh"
 
@@ -19,6 +19,7 @@ struct MeanshiftResult {
     float weight_sum;  // last sum of kernel weights (trial mode: the trial's weight sum)
     int used_iters;
     int n;             // pool size seen by the kernel
+    int trials_used;   // start-sample trials the reference's selection loop would have run (fused trial mode)
 };
 
 struct PoseMode {
