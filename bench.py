@@ -266,11 +266,21 @@ def bench_ours(args, rank, world, local_rank):
         avg_ms = sm.value / max(1, sl.value)
         peak, peak_src = _peaks()
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+        # DRAM traffic per launch of the same kernel from the committed `ncu --set full` capture (profiles/)
+        traffic, issue_pct = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_search_kernel.json")) as f:
+                cap = json.load(f)
+            traffic, issue_pct = cap.get("dram_bytes_per_launch"), cap.get("issue_active_pct")
+        except (OSError, ValueError):
+            pass
         roof = {"bound": "hbm", "kernel": "k_cost_and_random_search", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "launches_timed": sl.value,
-                "note": "compute(MUFU/FP32 powf)-bound kernel; HBM fraction reported as BASELINE.json asks, see "
-                        "DESIGN.md and profiles/ for the pipe utilisation"}
+                "issue_slots_busy_pct_ncu": issue_pct,
+                "note": "instruction-issue-bound kernel (6 powf + expf + logf + ~10 IEEE divisions per likelihood "
+                        "term, all pinned by bit-parity): HBM fraction reported as BASELINE.json asks; the window "
+                        "state is L2 resident; see DESIGN.md §6 and profiles/r01_ncu_search_kernel.md"}
         # kernel launches per window (counted once, outside the timed region, with the CUPTI-based profiler)
         try:
             from torch.profiler import ProfilerActivity, profile

@@ -96,6 +96,11 @@ void vb_profile_get(double* search_ms, long long* search_launches);
  * out5 = { mean-shift runs, their iterations, start-sample trials, robust-fit runs, their iterations }. */
 void vb_profile_counters(long long* out5);
 
+/* Profiling hook: per-phase clock64 totals of the robust-fit kernel (LU, E-step, level-1 sums, exchange barrier,
+ * level-2 sums, M-step) accumulated since process start; only collected when the environment variable
+ * VB_POSE_MODE_PHASES is set before the first call.  Returns 0, or 1 when not collected. */
+int vb_debug_pose_mode_phases(long long* out8);
+
 /* Test hook for the speculative use of the libc rand() stream by the fused mean-shift start-sample selection
  * (csrc/libc_rand.h): snapshot, draw `draw` numbers, rewind, draw `keep`.  Afterwards the process-wide stream must
  * be exactly `keep` draws past where it was.  Returns 0, or 1 if the state array could not be captured. */

@@ -43,6 +43,7 @@ int optimize_depth_gpu(float* h_flows[], float* h_rigidnesses[], float* h_o_rigi
     if (N > vb::kMaxFrames || N_dp > vb::kMaxPriorFrames) return (int)cudaErrorInvalidValue;
     vb::DepthEM& E = vb::global_depth_em();
     E.shared_flows = nullptr;
+    E.overlap_smoothing = false;  // ABI calls hand the raw maps back to the host after every step
     if (int e = E.ensure(w, h, N, N_dp)) return e;
     cudaStream_t s = E.stream;
 
@@ -261,6 +262,11 @@ DLL_EXPORT void vb_profile_get(double* search_ms, long long* search_launches) {
     vb::KernelProfile& p = vb::kernel_profile();
     if (search_ms) *search_ms = p.search_ms;
     if (search_launches) *search_launches = p.search_launches;
+}
+DLL_EXPORT int vb_debug_pose_mode_phases(long long* out8) {
+    vb::PoseMode& M = vb::global_pose_mode();
+    if (!M.d_phase_cycles) return 1;
+    return (int)cudaMemcpy(out8, M.d_phase_cycles, 8 * sizeof(long long), cudaMemcpyDeviceToHost);
 }
 DLL_EXPORT int vb_debug_rand_speculate(int draw, int keep) {
     vb::LibcRandSnapshot snap;

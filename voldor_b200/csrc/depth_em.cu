@@ -548,14 +548,15 @@ __global__ void __launch_bounds__(256) k_fb_posterior(StackView E, StackView F, 
     E.base[(size_t)layer * E.plane + (size_t)y * E.pitch + x] = hmm_posterior(f, b);
 }
 
-void fb_smooth_stack(StackView E, StackView F, StackView B, int layers, int w, int h, float s0_ems_prob,
+// E_in -> E_out (may alias: the reference smooths in place)
+void fb_smooth_stack(StackView E_in, StackView E, StackView F, StackView B, int layers, int w, int h, float s0_ems_prob,
                      float no_change_prob, cudaStream_t s) {
     HmmConst k;
     k.nc = no_change_prob;
     k.one_m_nc = 1.f - no_change_prob;
     k.s0e = s0_ems_prob;
     const dim3 pb(32, 8), pg(VB_DIV_CEIL(w, 32), VB_DIV_CEIL(h, 8), layers);
-    k_fb_rows<<<dim3(VB_DIV_CEIL(h, 32), layers, 2), 32, 0, s>>>(E, F, B, w, h, k);
+    k_fb_rows<<<dim3(VB_DIV_CEIL(h, 32), layers, 2), 32, 0, s>>>(E_in, F, B, w, h, k);
     k_fb_posterior<<<pg, pb, 0, s>>>(E, F, B, w, h);
     k_fb_cols<<<dim3(VB_DIV_CEIL(w, 128), layers, 2), 128, 0, s>>>(E, F, B, w, h, k);
     k_fb_posterior<<<pg, pb, 0, s>>>(E, F, B, w, h);
@@ -613,8 +614,39 @@ void launch_local(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC
 // host side
 // ------------------------------------------------------------------------------------------------
 int DepthEM::init_stream() {
-    if (!stream) VB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (!stream) {
+        VB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        VB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        VB_CUDA(cudaEventCreateWithFlags(&ev_rig_ready, cudaEventDisableTiming));
+        VB_CUDA(cudaEventCreateWithFlags(&ev_smooth_done, cudaEventDisableTiming));
+        cudaDeviceProp prop;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) n_sm = prop.multiProcessorCount;
+    }
     return 0;
+}
+
+void DepthEM::invalidate_smoothing() {
+    if (smooth_layers > 0 && stream) cudaStreamWaitEvent(stream, ev_smooth_done, 0);
+    smooth_layers = 0;
+}
+
+// Block height of the 1-thread-per-pixel search kernel: the kernel keeps 53 registers, i.e. at most 1170 resident
+// threads per SM; pick the shape whose grid fills the last wave best (tail balance on 148 SMs).
+static int pick_search_block_y(int w, int h, int n_sm) {
+    static const int forced = [] { const char* e = getenv("VB_SEARCH_BLOCK_Y"); return e ? atoi(e) : 0; }();
+    if (forced > 0 && forced <= 8) return forced;
+    const int cand[4] = {6, 5, 8, 4};
+    int best = 8;
+    double best_eff = -1;
+    for (int by : cand) {
+        const int per_sm = 1170 / (32 * by);
+        const double waves = (double)(VB_DIV_CEIL(w, 32) * VB_DIV_CEIL(h, by)) / ((double)per_sm * n_sm);
+        const double eff = waves / ceil(waves);
+        if (eff > best_eff + 1e-9) best_eff = eff, best = by;
+    }
+    return best;
 }
 
 int DepthEM::seed_rng() {
@@ -626,6 +658,7 @@ int DepthEM::seed_rng() {
 
 int DepthEM::ensure(int w_, int h_, int N, int N_dp) {
     if (init_stream()) return (int)cudaErrorUnknown;
+    invalidate_smoothing();  // the caller is about to (re)write the maps
     w = w_, h = h_;
     if (rng.ensure(w, h, 6, false)) {
         if (int e = seed_rng()) return e;
@@ -635,6 +668,7 @@ int DepthEM::ensure(int w_, int h_, int N, int N_dp) {
     if (N > 0) {
         if (!shared_flows) flows.ensure(w, h, N, true);
         rig.ensure(w, h, N, true);
+        rig_s.ensure(w, h, N, true);
     }
     if (N_dp > 0) {
         dp.ensure(w, h, N_dp, true);
@@ -667,19 +701,31 @@ int DepthEM::run(int N, int N_dp, const DepthHyper& hp, bool update_rigidness_on
     cudaStream_t s = stream;
     const dim3 pb(32, 8), pg(VB_DIV_CEIL(w, 32), VB_DIV_CEIL(h, 8));
 
+    // smoothing of the rigidness maps issued on the side stream at the end of the previous call (window pipeline)
+    const bool pre_smoothed = smooth_layers >= N && smooth_layers > 0 && smooth_s0 == hp.s0_ems_prob &&
+                              smooth_nc == hp.no_change_prob;
+    if (smooth_layers > 0) cudaStreamWaitEvent(s, ev_smooth_done, 0);
+    smooth_layers = 0;
+
     if (!update_rigidness_only) {
         if (hp.fb_smooth) {
             if (N > 0) {
+                // out of place: the E-step below rewrites every rigidness value, so the smoothed maps are only ever
+                // seen as the weights of this M-step (the reference smooths in place, fb_smooth.h:77-107)
                 StackView E{rig.ptr, rig.pitch, rig.layer_elems()};
+                StackView S{rig_s.ptr, rig_s.pitch, rig_s.layer_elems()};
                 StackView F{fb_fwd.ptr, fb_fwd.pitch, fb_fwd.layer_elems()};
                 StackView B{fb_bwd.ptr, fb_bwd.pitch, fb_bwd.layer_elems()};
-                fb_smooth_stack(E, F, B, N, w, h, hp.s0_ems_prob, hp.no_change_prob, s);
+                if (!pre_smoothed) fb_smooth_stack(E, S, F, B, N, w, h, hp.s0_ems_prob, hp.no_change_prob, s);
+                A.rig = rig_s.ptr;
             }
             if (N_dp > 0) {
+                // prior confidences stay in place: the E-step leaves them untouched where the prior has no depth,
+                // so smoothed values can survive
                 StackView E{dp_conf.ptr, A.dp_conf_pitch, A.dp_conf_plane};
                 StackView F{fb_fwd.ptr, fb_fwd.pitch, fb_fwd.layer_elems()};
                 StackView B{fb_bwd.ptr, fb_bwd.pitch, fb_bwd.layer_elems()};
-                fb_smooth_stack(E, F, B, N_dp, w, h, hp.s0_ems_prob, hp.no_change_prob, s);
+                fb_smooth_stack(E, E, F, B, N_dp, w, h, hp.s0_ems_prob, hp.no_change_prob, s);
             }
             VB_RETURN_IF_CUDA_ERROR();
         }
@@ -689,8 +735,7 @@ int DepthEM::run(int N, int N_dp, const DepthHyper& hp, bool update_rigidness_on
             cudaEventRecord(prof.ev0, s);
         }
         {
-            // block height of the search kernel: tunable for tail balance (148 SMs x resident blocks vs grid size)
-            static const int by = [] { const char* e = getenv("VB_SEARCH_BLOCK_Y"); return e ? atoi(e) : 8; }();
+            const int by = pick_search_block_y(w, h, n_sm);
             const dim3 sb(32, by), sg(VB_DIV_CEIL(w, 32), VB_DIV_CEIL(h, by));
             k_cost_and_random_search<<<sg, sb, 0, s>>>(A, cam, pcam, hp.n_rand_samples);
         }
@@ -717,8 +762,23 @@ int DepthEM::run(int N, int N_dp, const DepthHyper& hp, bool update_rigidness_on
         }
         VB_RETURN_IF_CUDA_ERROR();
     }
+    A.rig = rig.ptr;  // the E-step writes the raw posteriors
     k_update_rigidness<<<pg, pb, 0, s>>>(A, cam, pcam);
     VB_RETURN_IF_CUDA_ERROR();
+    if (overlap_smoothing && hp.fb_smooth && N > 0) {
+        // smooth the new rigidness maps for the next M-step on the side stream, concurrently with whatever the
+        // caller does next with the raw maps (the camera step of the next EM iteration only reads them)
+        VB_CUDA(cudaEventRecord(ev_rig_ready, s));
+        VB_CUDA(cudaStreamWaitEvent(side, ev_rig_ready, 0));
+        StackView E{rig.ptr, rig.pitch, rig.layer_elems()};
+        StackView S{rig_s.ptr, rig_s.pitch, rig_s.layer_elems()};
+        StackView F{fb_fwd.ptr, fb_fwd.pitch, fb_fwd.layer_elems()};
+        StackView B{fb_bwd.ptr, fb_bwd.pitch, fb_bwd.layer_elems()};
+        fb_smooth_stack(E, S, F, B, N, w, h, hp.s0_ems_prob, hp.no_change_prob, side);
+        VB_CUDA(cudaEventRecord(ev_smooth_done, side));
+        smooth_layers = N, smooth_s0 = hp.s0_ems_prob, smooth_nc = hp.no_change_prob;
+        VB_RETURN_IF_CUDA_ERROR();
+    }
     return 0;
 }
 

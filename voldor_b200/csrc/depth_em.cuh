@@ -23,7 +23,8 @@ struct DepthEM {
     int w = 0, h = 0;
     // device state
     TexStack<float2> flows;      // N layers, bilinear fetched
-    Plane<float> rig;            // N layers, rigidness maps W_f
+    Plane<float> rig;            // N layers, rigidness maps W_f (raw E-step posteriors)
+    Plane<float> rig_s;          // N layers, forward-backward smoothed copy = the weights of the M-step
     Plane<float> depth, cost;    // 1 layer each
     Plane<uint32_t> rng;         // 6 layers: XORWOW d, v0..v4 (SoA)
     TexStack<float> dp, dp_pconf, dp_conf;  // N_dp layers each, bilinear fetched
@@ -31,6 +32,17 @@ struct DepthEM {
     CamBlock cam;
     PriorCamBlock pcam;
     cudaStream_t stream = nullptr;
+    // Side stream for the smoothing of the rigidness maps: in the window pipeline it runs right after the E-step,
+    // concurrently with the next camera step (which reads the raw maps).  smooth_layers > 0 <=> rig_s holds (once
+    // ev_smooth_done fires) the smoothing of the current `rig` with these parameters.
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_rig_ready = nullptr, ev_smooth_done = nullptr;
+    bool overlap_smoothing = false;
+    int smooth_layers = 0;
+    float smooth_s0 = 0.f, smooth_nc = 0.f;
+    int n_sm = 148;
+    // call before anything else writes `rig` on `stream` (uploads, fills)
+    void invalidate_smoothing();
     // when set, kernels fetch flows from this stack instead of `flows` (window pipeline shares one upload)
     TexStack<float2>* shared_flows = nullptr;
 

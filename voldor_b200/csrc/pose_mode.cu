@@ -345,6 +345,7 @@ struct RobustArgs {
     int N, dims, max_iters;
     int slice_in_smem, centred_in_smem;
     const float* space;
+    long long* phase_cycles;  // optional [8]: per-phase clock64 totals of rank 0 (debug / profiling)
 };
 struct RobustResult {
     float mean[kRobustMaxDims];
@@ -401,6 +402,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     float weight = 0.f;  // sum of weights of the previous E-step (uniform over all threads)
     int state = 0;       // 0 continue, 1 converged, 2 unreliable (uniform)
     int iter = 0;
+    long long tick = clock64(), ph[6] = {0, 0, 0, 0, 0, 0};
+#define VB_PHASE(k)                                   \
+    do {                                              \
+        const long long now_ = clock64();             \
+        ph[k] += now_ - tick;                         \
+        tick = now_;                                  \
+    } while (0)
     for (iter = 0; iter < A.max_iters; iter++) {
         const Exchange X = exchange_for(iter, S.NB, s_part, 28, partials_g);
         if (warp == 0) {
@@ -486,6 +494,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
             if (lane == 0) s_lu_state = det > 0 ? 0 : 2;
         }
         __syncthreads();
+        VB_PHASE(0);
         if (s_lu_state == 2) {
             state = 2;
             break;
@@ -514,6 +523,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
             wv[li] = wgt;
         }
         __syncthreads();
+        VB_PHASE(1);
         // weighted moments, reference tree order
         tree_level1(S, Q, X, cluster, [&](int q, int li) {
             const float w = wv[li];
@@ -524,9 +534,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
             const float b = av ? av[(size_t)li * dims + d2] : f_sub(f_mul(S.x(li, d2), A.scale), s_mean[d2]);
             return f_mul(f_mul(w, a), b);
         });
+        VB_PHASE(2);
         exchange_sync(X, cluster);
+        VB_PHASE(3);
         tree_level2(S.NB, Q, X, sums);
         __syncthreads();
+        VB_PHASE(4);
         {
             // host part of the reference iteration (fit_robust_gaussian.cu:209-246); the decision is evaluated by
             // every thread, the divisions of the M-step by one thread per moment
@@ -544,8 +557,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
             }
         }
         __syncthreads();
+        VB_PHASE(5);
         if (state != 0) break;
     }
+#undef VB_PHASE
+    if (rank == 0 && t == 0 && A.phase_cycles)
+        for (int k = 0; k < 6; k++) A.phase_cycles[k] += ph[k];
     if (rank == 0 && t == 0) {
         out->reliable = (state != 2);
         out->used_iters = iter;
@@ -580,6 +597,10 @@ int PoseMode::init() {
     VB_CUDA(cudaMalloc((void**)&d_partials, (size_t)64 * kMaxTreeBlocks * sizeof(float)));
     VB_CUDA(cudaMalloc((void**)&d_rg_sums, 256 + kCluster * sizeof(int)));
     VB_CUDA(cudaMallocHost((void**)&h_rg_sums, 256));
+    if (getenv("VB_POSE_MODE_PHASES")) {
+        VB_CUDA(cudaMalloc((void**)&d_phase_cycles, 8 * sizeof(long long)));
+        VB_CUDA(cudaMemset(d_phase_cycles, 0, 8 * sizeof(long long)));
+    }
     VB_CUDA(cudaFuncSetAttribute(k_meanshift, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     VB_CUDA(cudaFuncSetAttribute(k_robust_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     return 0;
@@ -700,6 +721,7 @@ int PoseMode::fit_robust_gaussian(const float* d_space, int N, int dims, float s
     A.N = N, A.dims = dims, A.max_iters = max_iters, A.space = d_space;
     size_t smem_bytes;
     smem_plan(N, dims, A.slice_in_smem, smem_bytes, &A.centred_in_smem);
+    A.phase_cycles = d_phase_cycles;
     if (used_iters) *used_iters = 0;
 
     RobustResult* d_res = (RobustResult*)d_rg_sums;

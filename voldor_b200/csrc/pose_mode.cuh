@@ -32,6 +32,7 @@ struct PoseMode {
     size_t rg_capacity = 0;
     float* d_rg_sums = nullptr;  // RobustResult on the device
     float* h_rg_sums = nullptr;  // pinned mirror
+    long long* d_phase_cycles = nullptr;  // robust-fit phase clocks, allocated when VB_POSE_MODE_PHASES is set
 
     int init();
     // Mean-shift on d_space[N][dims]; N is read from d_n when non-null.  Blocks until the result is on the host

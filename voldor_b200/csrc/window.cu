@@ -212,6 +212,7 @@ struct Window {
         // device state; flows live once, in the depth step's stack, and the collector aliases them
         E.shared_flows = nullptr;
         if (int e = E.ensure(w, h, N, n_depth_priors)) return e;
+        E.overlap_smoothing = true;  // smoothing of iteration k+1's weights overlaps the camera step
         s = E.stream;
         if (int e = C.ensure(w, h, N)) return e;
         if (int e = M.init()) return e;
