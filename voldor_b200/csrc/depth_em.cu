@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(256)
 // (reference: optimize_depth.cu:209-235)
 // ------------------------------------------------------------------------------------------------
 enum { DIR_L2R = 0, DIR_T2B = 1, DIR_R2L = 2, DIR_B2T = 3 };
+constexpr int kLocalTermsPerLane = 1;  // default split of a candidate's likelihood terms over lanes
 
 template <int DIR>
 __global__ void __launch_bounds__(128)
@@ -260,58 +261,70 @@ __global__ void __launch_bounds__(128)
 // position of frame f depends on the in-view tests of all earlier frames (stale px1 rule).
 // The result is returned on every lane of the group.
 // ------------------------------------------------------------------------------------------------
-template <int G>
+template <int G, int TPL>
 __device__ __forceinline__ float pixel_cost_group(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC,
                                                   int px, int py, float depth, int gl, unsigned gmask, int gbase) {
+    // lane gl owns the terms k = gl, gl+G, ... (slot k/G); terms 0..N-1 are flows, N..N+N_dp-1 priors
     const float fpx = (float)px, fpy = (float)py;
     const float fw = (float)A.w, fh = (float)A.h;
     float ox, oy, oz;
     backproject(C, fpx, fpy, depth, ox, oy, oz);
     float px1 = fpx, py1 = fpy;
-    float m_px1 = 0, m_py1 = 0, m_px2 = 0, m_py2 = 0;
-    bool my_valid = false;
+    float m_px1[TPL], m_py1[TPL], m_px2[TPL], m_py2[TPL];
+    bool my_valid[TPL];
+    float my_w[TPL], my_log[TPL];
+#pragma unroll
+    for (int j = 0; j < TPL; j++) my_valid[j] = false, my_w[j] = 0.f, my_log[j] = 0.f, m_px1[j] = m_py1[j] = m_px2[j] = m_py2[j] = 0.f;
     for (int f = 0; f < A.N; f++) {
         float px2, py2;
         rigid_move(C.R[f], C.t[f], ox, oy, oz);
         project(C, ox, oy, oz, px2, py2);
         if (oz > 0 && px1 >= 0 && px1 < fw && py1 >= 0 && py1 < fh) {
-            if (f == gl) m_px1 = px1, m_py1 = py1, m_px2 = px2, m_py2 = py2, my_valid = true;
+#pragma unroll
+            for (int j = 0; j < TPL; j++)
+                if (f == gl + j * G) m_px1[j] = px1, m_py1[j] = py1, m_px2[j] = px2, m_py2[j] = py2, my_valid[j] = true;
             px1 = px2, py1 = py2;
         }
     }
-    float my_w = 0.f, my_log = 0.f;
-    if (my_valid) {
-        const float2 obs = fetch_stack<float2>(A.flows_tex, m_px1, m_py1, gl, A.h);
-        const float rfx = f_sub(m_px2, m_px1), rfy = f_sub(m_py2, m_py1);
-        my_w = A.rig[(size_t)gl * A.plane + (size_t)py * A.pitch + px];
-        my_log = logf(flow_rigidness(rfx, rfy, obs.x, obs.y, A.lambda, A.abs_rf));
-    }
-    const int pf = gl - A.N;
-    if (pf >= 0 && pf < A.N_dp) {
-        backproject(C, fpx, fpy, depth, ox, oy, oz);
-        rigid_move(PC.R[pf], PC.t[pf], ox, oy, oz);
-        project(C, ox, oy, oz, px1, py1);
-        if (oz > 0 && px1 >= 0 && px1 < fw && py1 >= 0 && py1 < fh) {
-            const float target_depth = fetch_stack<float>(A.dp_tex, px1, py1, pf, A.h);
-            const float target_pconf = fetch_stack<float>(A.dp_pconf_tex, px1, py1, pf, A.h);
-            const float target_conf = fetch_stack<float>(A.dp_conf_tex, px1, py1, pf, A.h);
-            if (target_depth > 0) {
-                const float scale = (A.disp_delta > 0 && pf == 0) ? A.disp_delta : A.delta;
-                my_w = f_mul(f_mul(target_pconf, target_conf), scale);
-                my_log = logf(depth_rigidness(oz, target_depth, A.basefocal, A.omega, A.abs_rf));
-                my_valid = true;
+#pragma unroll
+    for (int j = 0; j < TPL; j++) {
+        const int k = gl + j * G;
+        if (my_valid[j]) {
+            const float2 obs = fetch_stack<float2>(A.flows_tex, m_px1[j], m_py1[j], k, A.h);
+            const float rfx = f_sub(m_px2[j], m_px1[j]), rfy = f_sub(m_py2[j], m_py1[j]);
+            my_w[j] = A.rig[(size_t)k * A.plane + (size_t)py * A.pitch + px];
+            my_log[j] = logf(flow_rigidness(rfx, rfy, obs.x, obs.y, A.lambda, A.abs_rf));
+        }
+        const int pf = k - A.N;
+        if (pf >= 0 && pf < A.N_dp) {
+            backproject(C, fpx, fpy, depth, ox, oy, oz);
+            rigid_move(PC.R[pf], PC.t[pf], ox, oy, oz);
+            project(C, ox, oy, oz, px1, py1);
+            if (oz > 0 && px1 >= 0 && px1 < fw && py1 >= 0 && py1 < fh) {
+                const float target_depth = fetch_stack<float>(A.dp_tex, px1, py1, pf, A.h);
+                const float target_pconf = fetch_stack<float>(A.dp_pconf_tex, px1, py1, pf, A.h);
+                const float target_conf = fetch_stack<float>(A.dp_conf_tex, px1, py1, pf, A.h);
+                if (target_depth > 0) {
+                    const float scale = (A.disp_delta > 0 && pf == 0) ? A.disp_delta : A.delta;
+                    my_w[j] = f_mul(f_mul(target_pconf, target_conf), scale);
+                    my_log[j] = logf(depth_rigidness(oz, target_depth, A.basefocal, A.omega, A.abs_rf));
+                    my_valid[j] = true;
+                }
             }
         }
     }
     float cost_sum = 0.f, weight_sum = 0.f;
     const int terms = A.N + A.N_dp;
-    for (int k = 0; k < terms; k++) {
-        const float w = __shfl_sync(gmask, my_w, gbase + k);
-        const float lg = __shfl_sync(gmask, my_log, gbase + k);
-        const int v = __shfl_sync(gmask, (int)my_valid, gbase + k);
-        if (v) {
-            cost_sum = f_fma(-w, lg, cost_sum);
-            weight_sum = f_add(weight_sum, w);
+#pragma unroll
+    for (int j = 0; j < TPL; j++) {
+        for (int k = j * G; k < terms && k < (j + 1) * G; k++) {
+            const float w = __shfl_sync(gmask, my_w[j], gbase + k - j * G);
+            const float lg = __shfl_sync(gmask, my_log[j], gbase + k - j * G);
+            const int v = __shfl_sync(gmask, (int)my_valid[j], gbase + k - j * G);
+            if (v) {
+                cost_sum = f_fma(-w, lg, cost_sum);
+                weight_sum = f_add(weight_sum, w);
+            }
         }
     }
     if (weight_sum == 0) return INFINITY;
@@ -320,7 +333,7 @@ __device__ __forceinline__ float pixel_cost_group(const DepthView& A, const CamB
 
 // local propagation with G lanes per chain: block = 128 threads = 128/G chains.
 // chain index c -> (o, seg) with o fastest.
-template <int DIR, int G>
+template <int DIR, int G, int TPL>
 __global__ void __launch_bounds__(128)
     k_local_propagation_group(const DepthView A, const __grid_constant__ CamBlock C,
                               const __grid_constant__ PriorCamBlock PC, int width, int n_other, int n_seg) {
@@ -348,7 +361,7 @@ __global__ void __launch_bounds__(128)
     for (int i = 0, pos = first; i < count; i++, pos += step) {
         const int x = rowdir ? pos : o, y = rowdir ? o : pos;
         const size_t idx = (size_t)y * A.pitch + x;
-        const float c = pixel_cost_group<G>(A, C, PC, x, y, cand, gl, gmask, gbase);
+        const float c = pixel_cost_group<G, TPL>(A, C, PC, x, y, cand, gl, gmask, gbase);
         const float cur_cost = A.cost[idx];
         if (c < cur_cost) {
             if (gl == 0) A.depth[idx] = cand, A.cost[idx] = c;
@@ -579,11 +592,11 @@ void launch_global(const DepthView& A, const CamBlock& C, const PriorCamBlock& P
         k_global_propagation<DIR><<<dim3(VB_DIV_CEIL(n, 4), VB_DIV_CEIL(other, 32)), dim3(4, 32), 0, s>>>(A, C, PC, step);
 }
 
-template <int DIR, int G>
+template <int DIR, int G, int TPL>
 void launch_local_group(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC, int width, int other,
                         int nseg, cudaStream_t s) {
     const long long threads = (long long)other * nseg * G;
-    k_local_propagation_group<DIR, G><<<(unsigned)VB_DIV_CEIL(threads, 128), 128, 0, s>>>(A, C, PC, width, other, nseg);
+    k_local_propagation_group<DIR, G, TPL><<<(unsigned)VB_DIV_CEIL(threads, 128), 128, 0, s>>>(A, C, PC, width, other, nseg);
 }
 
 template <int DIR>
@@ -594,17 +607,34 @@ void launch_local(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC
     const int terms = A.N + A.N_dp;
     // one lane per likelihood term of a candidate (see pixel_cost_group); a 31-long chain then costs ~1 term of
     // latency per step instead of N
-    if (terms > 16 && terms <= 32)
-        launch_local_group<DIR, 32>(A, C, PC, width, other, nseg, s);
-    else if (terms > 8 && terms <= 16)
-        launch_local_group<DIR, 16>(A, C, PC, width, other, nseg, s);
-    else if (terms > 4)
-        launch_local_group<DIR, 8>(A, C, PC, width, other, nseg, s);
-    else if (terms > 2)
-        launch_local_group<DIR, 4>(A, C, PC, width, other, nseg, s);
-    else if (terms == 2)
-        launch_local_group<DIR, 2>(A, C, PC, width, other, nseg, s);
-    else
+    // lanes per chain G and terms per lane TPL (G * TPL >= terms).  One term per lane minimises the latency of a
+    // chain step; two terms per lane halve the warps and the redundant pose-chain walks — the better trade when
+    // the launch is issue bound.  VB_LOCAL_TPL overrides (profiling).
+    static const int forced_tpl = [] { const char* e = getenv("VB_LOCAL_TPL"); return e ? atoi(e) : 0; }();
+    const int tpl = forced_tpl > 0 ? forced_tpl : kLocalTermsPerLane;
+    const int lanes = VB_DIV_CEIL(terms, tpl);
+    const int G = lanes > 16 ? 32 : lanes > 8 ? 16 : lanes > 4 ? 8 : lanes > 2 ? 4 : lanes > 1 ? 2 : 1;
+#define VB_LOCAL_CASE(g)                                                              \
+    if (G == g) {                                                                     \
+        if (g >= terms)                                                               \
+            launch_local_group<DIR, g, 1>(A, C, PC, width, other, nseg, s);           \
+        else if (2 * g >= terms)                                                      \
+            launch_local_group<DIR, g, 2>(A, C, PC, width, other, nseg, s);           \
+        else                                                                          \
+            launch_local_group<DIR, g, 4>(A, C, PC, width, other, nseg, s);           \
+        return;                                                                       \
+    }
+    if (terms >= 2 && 4 * G >= terms) {
+        VB_LOCAL_CASE(32)
+        VB_LOCAL_CASE(16)
+        VB_LOCAL_CASE(8)
+        VB_LOCAL_CASE(4)
+        VB_LOCAL_CASE(2)
+    }
+#undef VB_LOCAL_CASE
+    if (terms >= 2 && G == 1) {
+        // a whole candidate per lane is what the plain kernel does
+    }
         k_local_propagation<DIR><<<dim3(VB_DIV_CEIL(other, 32), VB_DIV_CEIL(nseg, 4)), dim3(32, 4), 0, s>>>(A, C, PC, width);
 }
 

@@ -193,6 +193,9 @@ __device__ __forceinline__ void tree_level2(int NB, int Q, const Exchange& X, fl
 // ------------------------------------------------------------------------------------------------
 // mean-shift (reference: meanshift.cu:12-31 weights, :99-134 host loop)
 // ------------------------------------------------------------------------------------------------
+// FAST6: dims == 6 with the slice and the per-element products [Q][n_local] resident in shared memory — the
+// element loop is fully unrolled and every tree sum reads one conflict-free row.
+template <bool FAST6>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     k_meanshift(const MeanshiftArgs A, float* partials_g, MeanshiftResult* out) {
     extern __shared__ float smem[];
@@ -230,6 +233,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     if (S.nlb < 0) S.nlb = 0;
     float* wv = smem;  // weights of the local slice
     stage_slice(S, smem + (size_t)S.nlb * 512, A.slice_in_smem != 0);
+    const int n_local = S.nlb * 512;
+    float* prod = smem + (size_t)n_local * (1 + dims);  // FAST6: rows w, w*x_0 .. w*x_5
     const float two_var = f_add(A.kernel_var, A.kernel_var);  // 2*kernel_var
     if (threadIdx.x == 0) s_center_idx = A.center_idx, s_trials_used = 0;
     if (A.n_trials > 0) {
@@ -280,20 +285,47 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     for (int iter = 0; iter < n_iters; iter++) {
         const Exchange X = exchange_for(iter, S.NB, s_part, kMeanshiftQ, partials_g);
         // weights w_i = exp(-|x_i - mu|^2 / (2 var)) of the local slice
-        for (int li = threadIdx.x; li < S.nlb * 512; li += kThreads) {
-            float wgt = 0.f;
-            if (S.gidx(li) < N) {
-                float l2 = 0.f;
-                for (int d = 0; d < dims; d++) {
-                    const float diff = f_sub(S.x(li, d), c_mean[d]);
-                    l2 = f_fma(diff, diff, l2);
+        if constexpr (FAST6) {
+            float cm[6];
+#pragma unroll
+            for (int d = 0; d < 6; d++) cm[d] = c_mean[d];
+            for (int li = threadIdx.x; li < n_local; li += kThreads) {
+                float wgt = 0.f, x[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (S.gidx(li) < N) {
+                    float l2 = 0.f;
+#pragma unroll
+                    for (int d = 0; d < 6; d++) {
+                        x[d] = S.local[(size_t)li * 6 + d];
+                        const float diff = f_sub(x[d], cm[d]);
+                        l2 = f_fma(diff, diff, l2);
+                    }
+                    wgt = expf(f_div(-l2, two_var));
                 }
-                wgt = expf(f_div(-l2, two_var));
+                prod[li] = wgt;
+                if (Q > 1) {
+#pragma unroll
+                    for (int d = 0; d < 6; d++) prod[(size_t)(1 + d) * n_local + li] = f_mul(wgt, x[d]);
+                }
             }
-            wv[li] = wgt;
+            __syncthreads();
+            tree_level1(S, Q, X, cluster, [&](int q, int li) { return prod[(size_t)q * n_local + li]; });
+        } else {
+            for (int li = threadIdx.x; li < n_local; li += kThreads) {
+                float wgt = 0.f;
+                if (S.gidx(li) < N) {
+                    float l2 = 0.f;
+                    for (int d = 0; d < dims; d++) {
+                        const float diff = f_sub(S.x(li, d), c_mean[d]);
+                        l2 = f_fma(diff, diff, l2);
+                    }
+                    wgt = expf(f_div(-l2, two_var));
+                }
+                wv[li] = wgt;
+            }
+            __syncthreads();
+            tree_level1(S, Q, X, cluster,
+                        [&](int q, int li) { return q == 0 ? wv[li] : f_mul(wv[li], S.x(li, q - 1)); });
         }
-        __syncthreads();
-        tree_level1(S, Q, X, cluster, [&](int q, int li) { return q == 0 ? wv[li] : f_mul(wv[li], S.x(li, q - 1)); });
         exchange_sync(X, cluster);
         tree_level2(S.NB, Q, X, sums);
         __syncthreads();
@@ -361,6 +393,7 @@ __device__ __forceinline__ double d_add(double a, double b) { return __dadd_rn(a
 __device__ __forceinline__ double d_sub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double d_div(double a, double b) { return __ddiv_rn(a, b); }
 
+template <bool FAST6>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     k_robust_fit(const RobustArgs A, float* partials_g, RobustResult* out) {
     extern __shared__ float smem[];
@@ -390,7 +423,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     float* wv = smem;
     stage_slice(S, smem + (size_t)n_local, A.slice_in_smem != 0);
     // centred, scaled coordinates of the local slice (rewritten by every E-step)
-    float* av = A.centred_in_smem ? smem + (size_t)n_local * (1 + (A.slice_in_smem ? dims : 0)) : nullptr;
+    float* av = (!FAST6 && A.centred_in_smem) ? smem + (size_t)n_local * (1 + (A.slice_in_smem ? dims : 0)) : nullptr;
+    float* prod = smem + (size_t)n_local * (1 + dims);  // FAST6: rows w, w*x_d (6), w*a_d1*a_d2 (21)
     if (t == 0) {
         for (int d = 0; d < dims; d++) s_mean[d] = A.mean[d];
         for (int k = 0; k < cdims; k++) s_cov[k] = A.covar[k];
@@ -501,39 +535,81 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
         }
 
         // E-step weights: hard truncation of the Mahalanobis distance (fit_robust_gaussian.cu:67-86)
-        for (int li = t; li < n_local; li += kThreads) {
-            float wgt = 0.f;
-            if (S.gidx(li) < N) {
-                float diff[kRobustMaxDims];
-                for (int d = 0; d < dims; d++) diff[d] = f_sub(f_mul(S.x(li, d), A.scale), s_mean[d]);
+        if constexpr (FAST6) {
+            float mean[6], ci[21];
+#pragma unroll
+            for (int d = 0; d < 6; d++) mean[d] = s_mean[d];
+#pragma unroll
+            for (int k = 0; k < 21; k++) ci[k] = s_cinv[k];
+            for (int li = t; li < n_local; li += kThreads) {
+                if (S.gidx(li) >= N) continue;  // never read by the tree sums
+                float sx[6], a[6];
+#pragma unroll
+                for (int d = 0; d < 6; d++) {
+                    sx[d] = f_mul(S.local[(size_t)li * 6 + d], A.scale);
+                    a[d] = f_sub(sx[d], mean[d]);
+                }
                 float z = 0.f;
-                for (int d1 = 0; d1 < dims; d1++) {
+#pragma unroll
+                for (int d1 = 0; d1 < 6; d1++) {
                     float tmp = 0.f;
-                    for (int d2 = 0; d2 < dims; d2++) {
-                        const float ci = (d1 >= d2) ? s_cinv[(d1 * d1 + d1) / 2 + d2] : s_cinv[(d2 * d2 + d2) / 2 + d1];
-                        tmp = f_add(tmp, f_mul(ci, diff[d2]));
+#pragma unroll
+                    for (int d2 = 0; d2 < 6; d2++) {
+                        const float c = (d1 >= d2) ? ci[(d1 * d1 + d1) / 2 + d2] : ci[(d2 * d2 + d2) / 2 + d1];
+                        tmp = f_add(tmp, f_mul(c, a[d2]));
                     }
-                    z = f_fma(tmp, diff[d1], z);
+                    z = f_fma(tmp, a[d1], z);
                 }
                 z = __fsqrt_rn(z);
-                wgt = z < A.trunc_sigma ? 1.f : 0.f;
-                if (av)
-                    for (int d = 0; d < dims; d++) av[(size_t)li * dims + d] = diff[d];
+                const float w = z < A.trunc_sigma ? 1.f : 0.f;
+                prod[li] = w;
+#pragma unroll
+                for (int d = 0; d < 6; d++) prod[(size_t)(1 + d) * n_local + li] = f_mul(w, sx[d]);
+#pragma unroll
+                for (int d1 = 0; d1 < 6; d1++)
+#pragma unroll
+                    for (int d2 = 0; d2 <= d1; d2++)
+                        prod[(size_t)(7 + (d1 * d1 + d1) / 2 + d2) * n_local + li] = f_mul(f_mul(w, a[d1]), a[d2]);
             }
-            wv[li] = wgt;
+            __syncthreads();
+            VB_PHASE(1);
+            tree_level1(S, Q, X, cluster, [&](int q, int li) { return prod[(size_t)q * n_local + li]; });
+        } else {
+            for (int li = t; li < n_local; li += kThreads) {
+                float wgt = 0.f;
+                if (S.gidx(li) < N) {
+                    float diff[kRobustMaxDims];
+                    for (int d = 0; d < dims; d++) diff[d] = f_sub(f_mul(S.x(li, d), A.scale), s_mean[d]);
+                    float z = 0.f;
+                    for (int d1 = 0; d1 < dims; d1++) {
+                        float tmp = 0.f;
+                        for (int d2 = 0; d2 < dims; d2++) {
+                            const float ci =
+                                (d1 >= d2) ? s_cinv[(d1 * d1 + d1) / 2 + d2] : s_cinv[(d2 * d2 + d2) / 2 + d1];
+                            tmp = f_add(tmp, f_mul(ci, diff[d2]));
+                        }
+                        z = f_fma(tmp, diff[d1], z);
+                    }
+                    z = __fsqrt_rn(z);
+                    wgt = z < A.trunc_sigma ? 1.f : 0.f;
+                    if (av)
+                        for (int d = 0; d < dims; d++) av[(size_t)li * dims + d] = diff[d];
+                }
+                wv[li] = wgt;
+            }
+            __syncthreads();
+            VB_PHASE(1);
+            // weighted moments, reference tree order
+            tree_level1(S, Q, X, cluster, [&](int q, int li) {
+                const float w = wv[li];
+                if (q == 0) return w;
+                if (q <= dims) return f_mul(w, f_mul(S.x(li, q - 1), A.scale));
+                const int d1 = s_d1[q - 1 - dims], d2 = s_d2[q - 1 - dims];
+                const float a = av ? av[(size_t)li * dims + d1] : f_sub(f_mul(S.x(li, d1), A.scale), s_mean[d1]);
+                const float b = av ? av[(size_t)li * dims + d2] : f_sub(f_mul(S.x(li, d2), A.scale), s_mean[d2]);
+                return f_mul(f_mul(w, a), b);
+            });
         }
-        __syncthreads();
-        VB_PHASE(1);
-        // weighted moments, reference tree order
-        tree_level1(S, Q, X, cluster, [&](int q, int li) {
-            const float w = wv[li];
-            if (q == 0) return w;
-            if (q <= dims) return f_mul(w, f_mul(S.x(li, q - 1), A.scale));
-            const int d1 = s_d1[q - 1 - dims], d2 = s_d2[q - 1 - dims];
-            const float a = av ? av[(size_t)li * dims + d1] : f_sub(f_mul(S.x(li, d1), A.scale), s_mean[d1]);
-            const float b = av ? av[(size_t)li * dims + d2] : f_sub(f_mul(S.x(li, d2), A.scale), s_mean[d2]);
-            return f_mul(f_mul(w, a), b);
-        });
         VB_PHASE(2);
         exchange_sync(X, cluster);
         VB_PHASE(3);
@@ -573,13 +649,20 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
 }
 
 // shared-memory plan for a pool of at most n elements: weights + (if it fits) the slice of every CTA
-void smem_plan(int n, int dims, int& slice_in_smem, size_t& bytes, int* centred_in_smem = nullptr) {
+// fast_q > 0: also try to place the [fast_q][n_local] product rows of the FAST6 kernels (dims == 6 only)
+void smem_plan(int n, int dims, int& slice_in_smem, size_t& bytes, int* centred_in_smem, int fast_q, bool& fast6) {
     const int NB = (n + 511) / 512;
     const size_t nlb = (size_t)(NB + kCluster - 1) / kCluster;
     const size_t wb = nlb * 512 * sizeof(float);
     const size_t pb = nlb * 512 * dims * sizeof(float);
     slice_in_smem = (wb + pb <= kSmemBudget);
     bytes = wb + (slice_in_smem ? pb : 0);
+    fast6 = dims == 6 && fast_q > 0 && slice_in_smem && bytes + wb * fast_q <= kSmemBudget;
+    if (fast6) {
+        bytes += wb * fast_q;
+        if (centred_in_smem) *centred_in_smem = 0;
+        return;
+    }
     if (centred_in_smem) {
         *centred_in_smem = (bytes + pb <= kSmemBudget);
         if (*centred_in_smem) bytes += pb;
@@ -601,8 +684,10 @@ int PoseMode::init() {
         VB_CUDA(cudaMalloc((void**)&d_phase_cycles, 8 * sizeof(long long)));
         VB_CUDA(cudaMemset(d_phase_cycles, 0, 8 * sizeof(long long)));
     }
-    VB_CUDA(cudaFuncSetAttribute(k_meanshift, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    VB_CUDA(cudaFuncSetAttribute(k_robust_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    VB_CUDA(cudaFuncSetAttribute(k_meanshift<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    VB_CUDA(cudaFuncSetAttribute(k_meanshift<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    VB_CUDA(cudaFuncSetAttribute(k_robust_fit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    VB_CUDA(cudaFuncSetAttribute(k_robust_fit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     return 0;
 }
 
@@ -610,9 +695,13 @@ static int run_meanshift(PoseMode& M, MeanshiftArgs& A, int n_plan, float* h_io_
                          int* used_iters) {
     if (n_plan > 512 * 512) return (int)cudaErrorInvalidValue;
     size_t smem_bytes;
-    smem_plan(n_plan, A.dims, A.slice_in_smem, smem_bytes);
+    bool fast6;
+    smem_plan(n_plan, A.dims, A.slice_in_smem, smem_bytes, nullptr, A.trial_only ? 1 : A.dims + 1, fast6);
     A.src.cta_counts = (int*)((char*)M.d_rg_sums + 256);
-    k_meanshift<<<kCluster, kThreads, smem_bytes, M.stream>>>(A, M.d_partials, M.d_result);
+    if (fast6)
+        k_meanshift<true><<<kCluster, kThreads, smem_bytes, M.stream>>>(A, M.d_partials, M.d_result);
+    else
+        k_meanshift<false><<<kCluster, kThreads, smem_bytes, M.stream>>>(A, M.d_partials, M.d_result);
     VB_RETURN_IF_CUDA_ERROR();
     VB_CUDA(cudaMemcpyAsync(M.h_result, M.d_result, sizeof(MeanshiftResult), cudaMemcpyDeviceToHost, M.stream));
     VB_CUDA(cudaStreamSynchronize(M.stream));
@@ -720,13 +809,17 @@ int PoseMode::fit_robust_gaussian(const float* d_space, int N, int dims, float s
     A.trunc_sigma = trunc_sigma, A.scale = scale, A.covar_reg_lambda = covar_reg_lambda, A.epsilon = epsilon;
     A.N = N, A.dims = dims, A.max_iters = max_iters, A.space = d_space;
     size_t smem_bytes;
-    smem_plan(N, dims, A.slice_in_smem, smem_bytes, &A.centred_in_smem);
+    bool fast6;
+    smem_plan(N, dims, A.slice_in_smem, smem_bytes, &A.centred_in_smem, 1 + dims + (dims * dims + dims) / 2, fast6);
     A.phase_cycles = d_phase_cycles;
     if (used_iters) *used_iters = 0;
 
     RobustResult* d_res = (RobustResult*)d_rg_sums;
     RobustResult* h_res = (RobustResult*)h_rg_sums;
-    k_robust_fit<<<kCluster, kThreads, smem_bytes, stream>>>(A, d_partials, d_res);
+    if (fast6)
+        k_robust_fit<true><<<kCluster, kThreads, smem_bytes, stream>>>(A, d_partials, d_res);
+    else
+        k_robust_fit<false><<<kCluster, kThreads, smem_bytes, stream>>>(A, d_partials, d_res);
     VB_RETURN_IF_CUDA_ERROR();
     VB_CUDA(cudaMemcpyAsync(h_res, d_res, sizeof(RobustResult), cudaMemcpyDeviceToHost, stream));
     VB_CUDA(cudaStreamSynchronize(stream));
