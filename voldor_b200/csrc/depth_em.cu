@@ -46,8 +46,15 @@ struct DepthView {
 // ------------------------------------------------------------------------------------------------
 // cost of hypothesising `depth` at pixel (px,py)   (reference: optimize_depth.cu:140-198)
 // ------------------------------------------------------------------------------------------------
-__device__ float pixel_cost(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC, int px, int py,
-                            float depth) {
+// Frame 0 is always fetched at the pixel centre itself, so its observed flow, Fisk shape/scale and outlier density do
+// not depend on the candidate: callers that test several candidates per pixel pass them in (PRE0).
+struct Frame0Model {
+    float2 obs;
+    ObservedFlowModel m;
+};
+template <bool PRE0>
+__device__ __forceinline__ float pixel_cost_t(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC, int px,
+                                              int py, float depth, const Frame0Model* f0) {
     float cost_sum = 0.f;
     float weight_sum = 0.f;
     const float fpx = (float)px, fpy = (float)py;
@@ -63,11 +70,16 @@ __device__ float pixel_cost(const DepthView& A, const CamBlock& C, const PriorCa
         rigid_move(C.R[f], C.t[f], ox, oy, oz);
         project(C, ox, oy, oz, px2, py2);
         if (oz > 0 && px1 >= 0 && px1 < fw && py1 >= 0 && py1 < fh) {
-            const float2 obs = fetch_stack<float2>(A.flows_tex, px1, py1, f, A.h);
             const float rfx = f_sub(px2, px1), rfy = f_sub(py2, py1);
+            float r;
+            if (PRE0 && f == 0) {
+                r = flow_rigidness_given(rfx, rfy, f0->obs.x, f0->obs.y, f0->m, A.abs_rf);
+            } else {
+                const float2 obs = fetch_stack<float2>(A.flows_tex, px1, py1, f, A.h);
+                r = flow_rigidness(rfx, rfy, obs.x, obs.y, A.lambda, A.abs_rf);
+            }
             px1 = px2, py1 = py2;  // stale when the branch is not taken
             const float wgt = wgt_ptr[(size_t)f * A.plane];
-            const float r = flow_rigidness(rfx, rfy, obs.x, obs.y, A.lambda, A.abs_rf);
             cost_sum = f_fma(-wgt, logf(r), cost_sum);
             weight_sum = f_add(weight_sum, wgt);
         }
@@ -94,6 +106,11 @@ __device__ float pixel_cost(const DepthView& A, const CamBlock& C, const PriorCa
 
     if (weight_sum == 0) return INFINITY;
     return f_div(cost_sum, fmaxf(weight_sum, FLT_EPSILON));
+}
+
+__device__ float pixel_cost(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC, int px, int py,
+                            float depth) {
+    return pixel_cost_t<false>(A, C, PC, px, py, depth, nullptr);
 }
 
 __device__ __forceinline__ void try_candidate(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC, int x,
@@ -161,6 +178,13 @@ __global__ void __launch_bounds__(256)
     }
     float best_depth = A.depth[idx];
     float best_cost = 0.f;
+    Frame0Model f0;
+    f0.obs = make_float2(0.f, 0.f);
+    f0.m.k.c = f0.m.k.s = f0.m.mu = 0.f;
+    if (A.N > 0) {
+        f0.obs = fetch_stack<float2>(A.flows_tex, (float)x, (float)y, 0, A.h);
+        f0.m = observed_flow_model(f0.obs.x, f0.obs.y, A.lambda, A.abs_rf);
+    }
     for (int it = -1; it < n_rand; it++) {
         float cand = best_depth;
         if (it >= 0) {
@@ -168,7 +192,7 @@ __global__ void __launch_bounds__(256)
             // d = 1/(range_factor*U + 1/MAXIMUM_DEPTH)   (reference: optimize_depth.cu:273)
             cand = __frcp_rn(f_fma(A.range_factor, u, 1.0f / kMaximumDepth));
         }
-        const float c = pixel_cost(A, C, PC, x, y, cand);
+        const float c = pixel_cost_t<true>(A, C, PC, x, y, cand, &f0);
         if (it < 0 || c < best_cost) {
             best_depth = cand;
             best_cost = c;
@@ -662,17 +686,23 @@ void DepthEM::invalidate_smoothing() {
     smooth_layers = 0;
 }
 
-// Block height of the 1-thread-per-pixel search kernel: the kernel keeps 53 registers, i.e. at most 1170 resident
-// threads per SM; pick the shape whose grid fills the last wave best (tail balance on 148 SMs).
+// Block height of the 1-thread-per-pixel search kernel: pick the shape whose grid fills the last wave best
+// (tail balance on 148 SMs); resident blocks per SM come from the occupancy calculator.
 static int pick_search_block_y(int w, int h, int n_sm) {
     static const int forced = [] { const char* e = getenv("VB_SEARCH_BLOCK_Y"); return e ? atoi(e) : 0; }();
     if (forced > 0 && forced <= 8) return forced;
+    static int per_sm[9] = {0};
     const int cand[4] = {6, 5, 8, 4};
     int best = 8;
     double best_eff = -1;
     for (int by : cand) {
-        const int per_sm = 1170 / (32 * by);
-        const double waves = (double)(VB_DIV_CEIL(w, 32) * VB_DIV_CEIL(h, by)) / ((double)per_sm * n_sm);
+        if (!per_sm[by]) {
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_cost_and_random_search, 32 * by, 0) != cudaSuccess || nb < 1)
+                nb = 1;
+            per_sm[by] = nb;
+        }
+        const double waves = (double)(VB_DIV_CEIL(w, 32) * VB_DIV_CEIL(h, by)) / ((double)per_sm[by] * n_sm);
         const double eff = waves / ceil(waves);
         if (eff > best_eff + 1e-9) best_eff = eff, best = by;
     }
