@@ -36,7 +36,7 @@ span = ev[-1]["ts"] + ev[-1]["dur"] - ev[0]["ts"]
 gap_after = collections.defaultdict(lambda: [0, 0.0])
 per_kernel = collections.defaultdict(lambda: [0, 0.0])
 for i, e in enumerate(ev):
-    name = e["name"].split("(")[0].replace("void ", "").replace("vb::(anonymous namespace)::", "")
+    name = e["name"].replace("vb::(anonymous namespace)::", "").replace("void ", "").split("(")[0]
     per_kernel[name][0] += 1
     per_kernel[name][1] += e["dur"]
     if i + 1 < len(ev):
@@ -44,7 +44,17 @@ for i, e in enumerate(ev):
         if g > 0:
             gap_after[name][0] += 1
             gap_after[name][1] += g
-print(f"window wall {r['stats_ms'][0]:.2f} ms; GPU activity span {span / 1000:.2f} ms, busy {busy / 1000:.2f} ms, idle {(span - busy) / 1000:.2f} ms; {len(ev)} activities")
+iv = sorted((e["ts"], e["ts"] + e["dur"]) for e in ev)
+union, (cs, ce) = 0.0, iv[0]
+for a0, b0 in iv[1:]:
+    if a0 > ce:
+        union += ce - cs
+        cs, ce = a0, b0
+    else:
+        ce = max(ce, b0)
+union += ce - cs
+print(f"window wall {r['stats_ms'][0]:.2f} ms; GPU activity span {span / 1000:.2f} ms, sum of activities {busy / 1000:.2f} ms, "
+      f"GPU busy (union) {union / 1000:.2f} ms, idle {(span - union) / 1000:.2f} ms; {len(ev)} activities")
 print("busy by kernel (us):")
 for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][1])[:16]:
     print(f"  {k[:60]:60s} n={v[0]:5d} sum={v[1]:9.1f} avg={v[1] / v[0]:7.1f}")

@@ -44,7 +44,8 @@ struct PoolSource {
     float rvec_scale;
     float* pool_out;
     int* used_out;
-    int* cta_counts;  // [kCluster] scratch
+    int* cta_counts;       // [kCluster] scratch
+    const int* aux_count;  // optional device counter echoed into the result (saves the caller a separate copy)
 };
 
 struct MeanshiftArgs {
@@ -224,7 +225,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
         cluster.sync();  // every CTA of the cluster is resident before anyone stores into its shared memory
     }
     if (N <= 0) {
-        if (rank == 0 && threadIdx.x == 0) out->used_iters = 0, out->n = N, out->weight_sum = 0.f, out->confidence = 0.f;
+        if (rank == 0 && threadIdx.x == 0) {
+            out->used_iters = 0, out->n = N, out->weight_sum = 0.f, out->confidence = 0.f;
+            out->aux_count = A.src.aux_count ? *A.src.aux_count : 0;
+        }
         return;
     }
     Slice S;
@@ -362,6 +366,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
         out->weight_sum = s_wsum;
         out->used_iters = s_used_iters;
         out->trials_used = s_trials_used;
+        out->aux_count = A.src.aux_count ? *A.src.aux_count : 0;
         out->n = N;
     }
 }
@@ -782,7 +787,8 @@ int PoseMode::meanshift(const float* d_space, const float* h_space_for_init, con
 
 int PoseMode::meanshift_from_hypotheses(const float* d_rvecs, const float* d_tvecs, int n_poses, float rvec_scale,
                                         float* d_pool, int* d_used, int dims, float kernel_var, float* h_io_mean,
-                                        float* h_o_confidence, int* used_iters, float epsilon, int max_iters) {
+                                        float* h_o_confidence, int* used_iters, float epsilon, int max_iters,
+                                        const int* d_aux_count) {
     if (int e = init()) return e;
     MeanshiftArgs A;
     memset(&A, 0, sizeof(A));
@@ -791,6 +797,7 @@ int PoseMode::meanshift_from_hypotheses(const float* d_rvecs, const float* d_tve
     A.center_idx = -1, A.trial_only = 0;
     A.src.rvecs = d_rvecs, A.src.tvecs = d_tvecs, A.src.n_poses = n_poses, A.src.rvec_scale = rvec_scale;
     A.src.pool_out = d_pool, A.src.used_out = d_used;
+    A.src.aux_count = d_aux_count;
     if (used_iters) *used_iters = 0;
     return run_meanshift(*this, A, n_poses, h_io_mean, h_o_confidence, used_iters);
 }

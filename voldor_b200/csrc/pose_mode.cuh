@@ -19,6 +19,7 @@ struct MeanshiftResult {
     float weight_sum;  // last sum of kernel weights (trial mode: the trial's weight sum)
     int used_iters;
     int n;             // pool size seen by the kernel
+    int aux_count;     // echo of the caller's device counter (number of P3P instances in the window pipeline)
     int trials_used;   // start-sample trials the reference's selection loop would have run (fused trial mode)
 };
 
@@ -45,7 +46,8 @@ struct PoseMode {
     // (hypothesis order, rvec * rvec_scale) into d_pool / d_used and iterates on it in the same launch.
     int meanshift_from_hypotheses(const float* d_rvecs, const float* d_tvecs, int n_poses, float rvec_scale,
                                   float* d_pool, int* d_used, int dims, float kernel_var, float* h_io_mean,
-                                  float* h_o_confidence, int* used_iters, float epsilon, int max_iters);
+                                  float* h_o_confidence, int* used_iters, float epsilon, int max_iters,
+                                  const int* d_aux_count = nullptr);
     // Robust Gaussian fit on x = scale * d_space (scale folds the caller's pose scaling).
     int fit_robust_gaussian(const float* d_space, int N, int dims, float scale, float* h_io_mean,
                             float* h_io_covar, float trunc_sigma, float covar_reg_lambda, float* h_o_density,

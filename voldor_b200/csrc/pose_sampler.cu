@@ -23,137 +23,164 @@ struct CollectView {
     int depth_pitch;
     float* p2_map;
     float* p3_map;
-    int* block_counts;
 };
 
 __device__ __forceinline__ float quiet_nan() { return __int_as_float(0x7fffffff); }  // CUDART_NAN_F
 
-// one thread per pixel in raster order (reference: collect_p3p_instances.cu:70-145)
+// the P3P instance of one pixel, NaN where invalid (reference: collect_p3p_instances.cu:70-145)
+struct Instance {
+    float p2x, p2y, p3x, p3y, p3z;
+};
+__device__ __forceinline__ Instance pixel_instance(const CollectView& A, const CamBlock& C, const CollectParams& P,
+                                                   int i) {
+    float p2x = quiet_nan(), p2y = quiet_nan();
+    float p3x = quiet_nan(), p3y = quiet_nan(), p3z = quiet_nan();
+    const int x = i % A.w, y = i / A.w;
+    const float depth = A.depth[(size_t)y * A.depth_pitch + x];
+    const float* rig_px = A.rig + (size_t)y * A.rig_pitch + x;
+    bool ok = !(depth < P.sample_min_depth || (P.sample_max_depth > 0 && depth > P.sample_max_depth));
+    if (ok && P.rigidness_sum_thresh > (float)(A.N + 1)) {
+        // only reachable for thresholds above N+1; sequential sum as in the reference
+        float sum = 0;
+        for (int f = 0; f < A.N; f++) sum = f_add(sum, rig_px[(size_t)f * A.rig_plane]);
+        if (sum < P.rigidness_sum_thresh) ok = false;
+    }
+    int n_trace = 0;
+    if (ok) {
+        float trace_product = 1;
+        const int last = P.max_trace_on_flow > 0 ? max(0, P.active_idx - P.max_trace_on_flow + 1) : 0;
+        for (int f = P.active_idx; f >= last; f--) {
+            trace_product = f_mul(trace_product, rig_px[(size_t)f * A.rig_plane]);
+            if (trace_product > P.rigidness_thresh)
+                n_trace++;
+            else
+                break;
+        }
+        if (n_trace <= 0) ok = false;
+    }
+    if (ok) {
+        const float fw = (float)A.w, fh = (float)A.h;
+        bool out_of_view = false;
+        float px = 0, py = 0, ox, oy, oz;
+        backproject(C, (float)x, (float)y, depth, ox, oy, oz);
+        const int first_traced = P.active_idx - n_trace + 1;
+        for (int f = 0; f <= P.active_idx; f++) {
+            if (f >= first_traced) {
+                if (f == first_traced) project(C, ox, oy, oz, px, py);
+                if (px > 0 && px < fw && py > 0 && py < fh) {  // strict > 0 here
+                    const float2 d2 = fetch_stack<float2>(A.flows_tex, px, py, f, A.h);
+                    px = f_add(px, d2.x);
+                    py = f_add(py, d2.y);
+                } else {
+                    out_of_view = true;
+                    break;
+                }
+            }
+            if (f < P.active_idx) rigid_move(C.R[f], C.t[f], ox, oy, oz);
+        }
+        if (!out_of_view && oz > P.sample_min_depth && (P.sample_max_depth <= 0 || oz < P.sample_max_depth)) {
+            p2x = px, p2y = py;
+            p3x = ox, p3y = oy, p3z = oz;
+        }
+    }
+    return Instance{p2x, p2y, p3x, p3y, p3z};
+}
+// validity rule of the host compaction loop (reference: voldor/geometry.cpp:72)
+__device__ __forceinline__ bool instance_valid(const Instance& v) {
+    return isfinite(f_add(f_add(f_add(f_add(v.p2x, v.p2y), v.p3x), v.p3y), v.p3z));
+}
+
+// one thread per pixel in raster order: dense NaN-filled maps (the ABI's output layout)
 __global__ void __launch_bounds__(kBlock)
     k_collect(const CollectView A, const __grid_constant__ CamBlock C, const CollectParams P) {
     const int i = blockIdx.x * kBlock + threadIdx.x;
     const int npx = A.w * A.h;
-    float p2x = quiet_nan(), p2y = quiet_nan();
-    float p3x = quiet_nan(), p3y = quiet_nan(), p3z = quiet_nan();
-
+    Instance v{quiet_nan(), quiet_nan(), quiet_nan(), quiet_nan(), quiet_nan()};
     if (i < npx) {
-        const int x = i % A.w, y = i / A.w;
-        const float depth = A.depth[(size_t)y * A.depth_pitch + x];
-        const float* rig_px = A.rig + (size_t)y * A.rig_pitch + x;
-        bool ok = !(depth < P.sample_min_depth || (P.sample_max_depth > 0 && depth > P.sample_max_depth));
-        if (ok && P.rigidness_sum_thresh > (float)(A.N + 1)) {
-            // only reachable for thresholds above N+1; sequential sum as in the reference
-            float sum = 0;
-            for (int f = 0; f < A.N; f++) sum = f_add(sum, rig_px[(size_t)f * A.rig_plane]);
-            if (sum < P.rigidness_sum_thresh) ok = false;
-        }
-        int n_trace = 0;
-        if (ok) {
-            float trace_product = 1;
-            const int last = P.max_trace_on_flow > 0 ? max(0, P.active_idx - P.max_trace_on_flow + 1) : 0;
-            for (int f = P.active_idx; f >= last; f--) {
-                trace_product = f_mul(trace_product, rig_px[(size_t)f * A.rig_plane]);
-                if (trace_product > P.rigidness_thresh)
-                    n_trace++;
-                else
-                    break;
-            }
-            if (n_trace <= 0) ok = false;
-        }
-        if (ok) {
-            const float fw = (float)A.w, fh = (float)A.h;
-            bool out_of_view = false;
-            float px = 0, py = 0, ox, oy, oz;
-            backproject(C, (float)x, (float)y, depth, ox, oy, oz);
-            const int first_traced = P.active_idx - n_trace + 1;
-            for (int f = 0; f <= P.active_idx; f++) {
-                if (f >= first_traced) {
-                    if (f == first_traced) project(C, ox, oy, oz, px, py);
-                    if (px > 0 && px < fw && py > 0 && py < fh) {  // strict > 0 here
-                        const float2 d2 = fetch_stack<float2>(A.flows_tex, px, py, f, A.h);
-                        px = f_add(px, d2.x);
-                        py = f_add(py, d2.y);
-                    } else {
-                        out_of_view = true;
-                        break;
-                    }
-                }
-                if (f < P.active_idx) rigid_move(C.R[f], C.t[f], ox, oy, oz);
-            }
-            if (!out_of_view && oz > P.sample_min_depth && (P.sample_max_depth <= 0 || oz < P.sample_max_depth)) {
-                p2x = px, p2y = py;
-                p3x = ox, p3y = oy, p3z = oz;
-            }
-        }
-        A.p2_map[2 * (size_t)i] = p2x;
-        A.p2_map[2 * (size_t)i + 1] = p2y;
-        A.p3_map[3 * (size_t)i] = p3x;
-        A.p3_map[3 * (size_t)i + 1] = p3y;
-        A.p3_map[3 * (size_t)i + 2] = p3z;
-    }
-    if (A.block_counts) {
-        // validity rule of the host compaction loop (reference: voldor/geometry.cpp:72)
-        const float s = f_add(f_add(f_add(f_add(p2x, p2y), p3x), p3y), p3z);
-        const int cnt = __syncthreads_count(isfinite(s) ? 1 : 0);
-        if (threadIdx.x == 0) A.block_counts[blockIdx.x] = cnt;
+        v = pixel_instance(A, C, P, i);
+        A.p2_map[2 * (size_t)i] = v.p2x;
+        A.p2_map[2 * (size_t)i + 1] = v.p2y;
+        A.p3_map[3 * (size_t)i] = v.p3x;
+        A.p3_map[3 * (size_t)i + 1] = v.p3y;
+        A.p3_map[3 * (size_t)i + 2] = v.p3z;
     }
 }
 
-// exclusive scan of per-block counts (single block)
-__global__ void __launch_bounds__(1024) k_scan_counts(const int* counts, int* offsets, int nblocks, int* total) {
-    __shared__ int warp_sums[32];
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int base = 0; base < nblocks; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int v = i < nblocks ? counts[i] : 0;
-        int incl = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        if (lane == 31) warp_sums[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            int ws = warp_sums[lane];
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(0xffffffffu, ws, o);
-                if (lane >= o) ws += n;
-            }
-            warp_sums[lane] = ws;
-        }
-        __syncthreads();
-        const int prefix = carry + (wid > 0 ? warp_sums[wid - 1] : 0) + incl - v;
-        if (i < nblocks) offsets[i] = prefix;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = prefix + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total = carry;
+// ------------------------------------------------------------------------------------------------
+// Single-pass collection + raster-order compaction (window pipeline: the dense maps are never needed there).
+// Replaces the reference's map kernel + D2H + host loop (voldor/geometry.cpp:70-80) with one launch: blocks take
+// raster tiles in ticket order and obtain their output offset by decoupled look-back over the descriptors
+// {epoch | status | count} published by their predecessors, so the instance order is exactly the raster order.
+// Descriptors carry a launch epoch, so nothing has to be cleared between launches.
+// ------------------------------------------------------------------------------------------------
+struct ScanState {
+    unsigned long long* desc;  // one per tile
+    unsigned int* ticket;      // running tile counter
+    unsigned int ticket_base;  // value of *ticket when this launch starts
+    unsigned int epoch;        // 1.. , never 0
+};
+__device__ __forceinline__ unsigned long long scan_pack(unsigned epoch, unsigned status, unsigned value) {
+    return ((unsigned long long)epoch << 34) | ((unsigned long long)status << 32) | value;
 }
+enum { SCAN_AGGREGATE = 1, SCAN_INCLUSIVE = 2 };
 
-// scatter valid instances to their raster-order rank (reference: voldor/geometry.cpp:70-80)
 __global__ void __launch_bounds__(kBlock)
-    k_compact(const float* p2_map, const float* p3_map, const int* offsets, int npx, float* p2c, float* p3c) {
+    k_collect_compact(const CollectView A, const __grid_constant__ CamBlock C, const CollectParams P, ScanState S,
+                      float* p2c, float* p3c, int* total) {
+    __shared__ unsigned s_tile;
     __shared__ int warp_counts[kBlock / 32];
-    const int i = blockIdx.x * kBlock + threadIdx.x;
-    float a = quiet_nan(), b = 0, c = 0, d = 0, e = 0;
-    if (i < npx) {
-        a = p2_map[2 * (size_t)i], b = p2_map[2 * (size_t)i + 1];
-        c = p3_map[3 * (size_t)i], d = p3_map[3 * (size_t)i + 1], e = p3_map[3 * (size_t)i + 2];
-    }
-    const bool valid = isfinite(f_add(f_add(f_add(f_add(a, b), c), d), e));
+    __shared__ int s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(S.ticket, 1u) - S.ticket_base;
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const int npx = A.w * A.h;
+    const int i = (int)tile * kBlock + threadIdx.x;
+    Instance v{quiet_nan(), quiet_nan(), quiet_nan(), quiet_nan(), quiet_nan()};
+    if (i < npx) v = pixel_instance(A, C, P, i);
+    const bool valid = instance_valid(v);
     const unsigned m = __ballot_sync(0xffffffffu, valid);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) warp_counts[wid] = __popc(m);
     __syncthreads();
-    int rank = offsets[blockIdx.x] + __popc(m & ((1u << lane) - 1u));
+    if (wid == 0) {
+        int cnt = 0;
+        for (int k = 0; k < kBlock / 32; k++) cnt += warp_counts[k];
+        volatile unsigned long long* desc = S.desc;
+        if (lane == 0)
+            desc[tile] = scan_pack(S.epoch, tile == 0 ? SCAN_INCLUSIVE : SCAN_AGGREGATE, (unsigned)cnt);
+        // look back over the predecessors, 32 at a time
+        int prefix = 0;
+        int j = (int)tile - 1 - lane;
+        bool done = tile == 0;
+        while (!done) {
+            unsigned long long d = 0;
+            bool ready;
+            do {
+                d = j >= 0 ? desc[j] : scan_pack(S.epoch, SCAN_INCLUSIVE, 0);
+                ready = (unsigned)(d >> 34) == S.epoch && ((d >> 32) & 3u) != 0;
+            } while (__any_sync(0xffffffffu, !ready));
+            const bool incl = ((d >> 32) & 3u) == SCAN_INCLUSIVE;
+            const unsigned incl_mask = __ballot_sync(0xffffffffu, incl);
+            // lanes up to (and including) the nearest inclusive predecessor contribute
+            const int first_incl = incl_mask ? __ffs(incl_mask) - 1 : 32;
+            int contrib = lane <= first_incl ? (int)(unsigned)(d & 0xffffffffu) : 0;
+            for (int o = 16; o >= 1; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+            prefix += contrib;
+            done = incl_mask != 0;
+            j -= 32;
+        }
+        if (lane == 0) {
+            if (tile != 0) desc[tile] = scan_pack(S.epoch, SCAN_INCLUSIVE, (unsigned)(prefix + cnt));
+            s_prefix = prefix;
+            if ((int)tile == (npx + kBlock - 1) / kBlock - 1) *total = prefix + cnt;
+        }
+    }
+    __syncthreads();
+    int rank = s_prefix + __popc(m & ((1u << lane) - 1u));
     for (int k = 0; k < wid; k++) rank += warp_counts[k];
     if (valid) {
-        p2c[2 * (size_t)rank] = a, p2c[2 * (size_t)rank + 1] = b;
-        p3c[3 * (size_t)rank] = c, p3c[3 * (size_t)rank + 1] = d, p3c[3 * (size_t)rank + 2] = e;
+        p2c[2 * (size_t)rank] = v.p2x, p2c[2 * (size_t)rank + 1] = v.p2y;
+        p3c[3 * (size_t)rank] = v.p3x, p3c[3 * (size_t)rank + 1] = v.p3y, p3c[3 * (size_t)rank + 2] = v.p3z;
     }
 }
 
@@ -260,8 +287,7 @@ int Collector::ensure(int w_, int h_, int N) {
     w = w_, h = h_;
     const int npx = w * h;
     if (npx > map_capacity) {
-        if (p2_map) cudaFree(p2_map), cudaFree(p3_map), cudaFree(p2c), cudaFree(p3c), cudaFree(block_counts),
-            cudaFree(block_offsets);
+        if (p2_map) cudaFree(p2_map), cudaFree(p3_map), cudaFree(p2c), cudaFree(p3c);
         if (!d_count) VB_CUDA(cudaMalloc((void**)&d_count, sizeof(int)));
         VB_CUDA(cudaMalloc((void**)&p2_map, (size_t)npx * 2 * sizeof(float)));
         VB_CUDA(cudaMalloc((void**)&p3_map, (size_t)npx * 3 * sizeof(float)));
@@ -270,8 +296,14 @@ int Collector::ensure(int w_, int h_, int N) {
         VB_CUDA(cudaMemset(p2c, 0, ((size_t)npx + 1) * 2 * sizeof(float)));
         VB_CUDA(cudaMemset(p3c, 0, ((size_t)npx + 1) * 3 * sizeof(float)));
         const int nb = VB_DIV_CEIL(npx, kBlock);
-        VB_CUDA(cudaMalloc((void**)&block_counts, nb * sizeof(int)));
-        VB_CUDA(cudaMalloc((void**)&block_offsets, nb * sizeof(int)));
+        if (scan_desc) cudaFree(scan_desc);
+        VB_CUDA(cudaMalloc((void**)&scan_desc, nb * sizeof(unsigned long long)));
+        VB_CUDA(cudaMemset(scan_desc, 0, nb * sizeof(unsigned long long)));
+        if (!scan_ticket) {
+            VB_CUDA(cudaMalloc((void**)&scan_ticket, sizeof(unsigned int)));
+            VB_CUDA(cudaMemset(scan_ticket, 0, sizeof(unsigned int)));
+        }
+        VB_CUDA(cudaDeviceSynchronize());  // the memsets run on the legacy stream, the kernels on `stream`
         map_capacity = npx;
     }
     (void)N;
@@ -291,16 +323,19 @@ int Collector::collect(int N, const CollectParams& P, bool compact) {
     A.rig = rig, A.rig_pitch = rig_pitch, A.rig_plane = rig_plane;
     A.depth = depth, A.depth_pitch = depth_pitch;
     A.p2_map = p2_map, A.p3_map = p3_map;
-    A.block_counts = compact ? block_counts : nullptr;
     const int npx = w * h;
     const int nb = VB_DIV_CEIL(npx, kBlock);
-    k_collect<<<nb, kBlock, 0, stream>>>(A, cam, P);
-    VB_RETURN_IF_CUDA_ERROR();
     if (compact) {
-        k_scan_counts<<<1, 1024, 0, stream>>>(block_counts, block_offsets, nb, d_count);
-        k_compact<<<nb, kBlock, 0, stream>>>(p2_map, p3_map, block_offsets, npx, p2c, p3c);
-        VB_RETURN_IF_CUDA_ERROR();
+        ScanState S;
+        S.desc = scan_desc, S.ticket = scan_ticket;
+        S.ticket_base = ticket_total, S.epoch = ++scan_epoch;
+        if (scan_epoch >= (1u << 30)) scan_epoch = 0;  // descriptors hold 30 epoch bits; 0 is never issued
+        ticket_total += (unsigned)nb;
+        k_collect_compact<<<nb, kBlock, 0, stream>>>(A, cam, P, S, p2c, p3c, d_count);
+    } else {
+        k_collect<<<nb, kBlock, 0, stream>>>(A, cam, P);
     }
+    VB_RETURN_IF_CUDA_ERROR();
     return 0;
 }
 

@@ -35,9 +35,11 @@ struct Collector {
     float* p3_map = nullptr;  // [h*w][3]
     float* p2c = nullptr;     // compacted instances (raster order), capacity w*h+1
     float* p3c = nullptr;
-    int* block_counts = nullptr;
-    int* block_offsets = nullptr;
     int* d_count = nullptr;  // number of compacted instances
+    // single-pass compaction state (decoupled look-back): tile descriptors, ticket counter, launch epoch
+    unsigned long long* scan_desc = nullptr;
+    unsigned int* scan_ticket = nullptr;
+    unsigned int ticket_total = 0, scan_epoch = 0;
     int map_capacity = 0;
     cudaStream_t stream = nullptr;
 

@@ -362,16 +362,15 @@ struct Window {
                             cfg.meanshift_max_iters, cfg.meanshift_max_init_trials, cfg.meanshift_good_init_confidence))
                 return -1;
         } else {
-            cudaMemcpyAsync(&sc.h_counts[0], C.d_count, sizeof(int), cudaMemcpyDeviceToHost, s);
             float density = cam.pose_density;
             int ms_iters = cam.last_used_ms_iters;
             float mean_io[6];
             memcpy(mean_io, pose_opm, sizeof(mean_io));
             if (M.meanshift_from_hypotheses(sc.rvecs, sc.tvecs, cfg.n_poses_to_sample, cfg.meanshift_rvec_scale, sc.pool,
                                             sc.d_used, 6, cfg.meanshift_kernel_var, mean_io, &density, &ms_iters,
-                                            cfg.meanshift_epsilon, cfg.meanshift_max_iters))
+                                            cfg.meanshift_epsilon, cfg.meanshift_max_iters, C.d_count))
                 return -1;
-            n_points = sc.h_counts[0];
+            n_points = M.h_result->aux_count;
             pool_used = M.h_result->n;
             if (n_points < 4) return 0;
             if (pool_used == 0) return 0;
