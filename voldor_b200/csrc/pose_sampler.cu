@@ -12,6 +12,7 @@ namespace vb {
 namespace {
 
 constexpr int kBlock = 256;
+constexpr int kCompactTile = 512;  // pixels per tile of the single-pass compaction (shorter look-back chain)
 
 struct CollectView {
     int N, w, h;
@@ -124,17 +125,18 @@ __device__ __forceinline__ unsigned long long scan_pack(unsigned epoch, unsigned
 }
 enum { SCAN_AGGREGATE = 1, SCAN_INCLUSIVE = 2 };
 
-__global__ void __launch_bounds__(kBlock)
+template <int TILE>
+__global__ void __launch_bounds__(TILE)
     k_collect_compact(const CollectView A, const __grid_constant__ CamBlock C, const CollectParams P, ScanState S,
                       float* p2c, float* p3c, int* total) {
     __shared__ unsigned s_tile;
-    __shared__ int warp_counts[kBlock / 32];
+    __shared__ int warp_counts[TILE / 32];
     __shared__ int s_prefix;
     if (threadIdx.x == 0) s_tile = atomicAdd(S.ticket, 1u) - S.ticket_base;
     __syncthreads();
     const unsigned tile = s_tile;
     const int npx = A.w * A.h;
-    const int i = (int)tile * kBlock + threadIdx.x;
+    const int i = (int)tile * TILE + threadIdx.x;
     Instance v{quiet_nan(), quiet_nan(), quiet_nan(), quiet_nan(), quiet_nan()};
     if (i < npx) v = pixel_instance(A, C, P, i);
     const bool valid = instance_valid(v);
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(kBlock)
     __syncthreads();
     if (wid == 0) {
         int cnt = 0;
-        for (int k = 0; k < kBlock / 32; k++) cnt += warp_counts[k];
+        for (int k = 0; k < TILE / 32; k++) cnt += warp_counts[k];
         volatile unsigned long long* desc = S.desc;
         if (lane == 0)
             desc[tile] = scan_pack(S.epoch, tile == 0 ? SCAN_INCLUSIVE : SCAN_AGGREGATE, (unsigned)cnt);
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(kBlock)
         if (lane == 0) {
             if (tile != 0) desc[tile] = scan_pack(S.epoch, SCAN_INCLUSIVE, (unsigned)(prefix + cnt));
             s_prefix = prefix;
-            if ((int)tile == (npx + kBlock - 1) / kBlock - 1) *total = prefix + cnt;
+            if ((int)tile == (npx + TILE - 1) / TILE - 1) *total = prefix + cnt;
         }
     }
     __syncthreads();
@@ -330,8 +332,9 @@ int Collector::collect(int N, const CollectParams& P, bool compact) {
         S.desc = scan_desc, S.ticket = scan_ticket;
         S.ticket_base = ticket_total, S.epoch = ++scan_epoch;
         if (scan_epoch >= (1u << 30)) scan_epoch = 0;  // descriptors hold 30 epoch bits; 0 is never issued
-        ticket_total += (unsigned)nb;
-        k_collect_compact<<<nb, kBlock, 0, stream>>>(A, cam, P, S, p2c, p3c, d_count);
+        const int nt = VB_DIV_CEIL(npx, kCompactTile);
+        ticket_total += (unsigned)nt;
+        k_collect_compact<kCompactTile><<<nt, kCompactTile, 0, stream>>>(A, cam, P, S, p2c, p3c, d_count);
     } else {
         k_collect<<<nb, kBlock, 0, stream>>>(A, cam, P);
     }
