@@ -65,7 +65,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -327,7 +327,7 @@ def bench_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu-port"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")

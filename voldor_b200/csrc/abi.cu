@@ -13,8 +13,6 @@
 
 namespace {
 
-std::mutex g_depth_mutex, g_collect_mutex, g_p3p_mutex, g_mode_mutex;
-
 // grow-only device scratch
 struct DevBuf {
     float* ptr = nullptr;
@@ -39,7 +37,7 @@ int optimize_depth_gpu(float* h_flows[], float* h_rigidnesses[], float* h_o_rigi
                        int n_rand_samples, int global_prop_step, int local_prop_width, float lambda, float omega,
                        float disp_delta, float delta, bool fb_smooth, float s0_ems_prob, float no_change_prob,
                        float range_factor, bool update_rigidness_only) {
-    std::lock_guard<std::mutex> lock(g_depth_mutex);
+    std::lock_guard<std::recursive_mutex> lock(vb::state_mutex());
     if (N > vb::kMaxFrames || N_dp > vb::kMaxPriorFrames) return (int)cudaErrorInvalidValue;
     vb::DepthEM& E = vb::global_depth_em();
     E.shared_flows = nullptr;
@@ -96,7 +94,7 @@ int collect_p3p_instances(float* h_flows[], float* h_rigidnesses[], float* h_dep
                           float* h_ts[], float* h_o_p2_map, float* h_o_p3_map, int N, int w, int h, int active_idx,
                           float rigidness_thresh, float rigidness_sum_thresh, float sample_min_depth,
                           float sample_max_depth, int max_trace_on_flow) {
-    std::lock_guard<std::mutex> lock(g_collect_mutex);
+    std::lock_guard<std::recursive_mutex> lock(vb::state_mutex());
     if (N > vb::kMaxFrames) return (int)cudaErrorInvalidValue;
     vb::Collector& C = vb::global_collector();
     if (int e = C.ensure(w, h, N)) return e;
@@ -136,7 +134,7 @@ int collect_p3p_instances(float* h_flows[], float* h_rigidnesses[], float* h_dep
 // ---------------------------------------------------------------------------------------------------
 static int solve_batch_host(float* h_p3s, float* h_p2s, float* h_o_rvecs, float* h_o_tvecs, float* h_K, int N_pts,
                             int N_poses, bool ap3p) {
-    std::lock_guard<std::mutex> lock(g_p3p_mutex);
+    std::lock_guard<std::recursive_mutex> lock(vb::state_mutex());
     static DevBuf p2, p3, rv, tv;
     static float K4[4] = {0, 0, 0, 0};  // fx, fy, cx, cy survive a NULL h_K like the reference's constants
     static cudaStream_t s = nullptr;
@@ -173,7 +171,7 @@ int solve_batch_p3p_lambdatwist_gpu(float* h_p3s, float* h_p2s, float* h_o_rvecs
 int meanshift_gpu(float* h_space, float kernel_var, float* h_io_mean, float* h_o_confidence, int* used_iters,
                   bool use_external_init_mean, int N, int dims, float epsilon, int max_iters, int max_init_trials,
                   float good_init_confidence) {
-    std::lock_guard<std::mutex> lock(g_mode_mutex);
+    std::lock_guard<std::recursive_mutex> lock(vb::state_mutex());
     static DevBuf space;
     vb::PoseMode& M = vb::global_pose_mode();
     if (int e = M.init()) return e;
@@ -186,7 +184,7 @@ int meanshift_gpu(float* h_space, float kernel_var, float* h_io_mean, float* h_o
 int fit_robust_gaussian(float* h_space, float* h_io_mean, float* h_io_covar, float trunc_sigma,
                         float covar_reg_lambda, float* h_o_density, int* used_iters, int N, int dims, float epsilon,
                         int max_iters) {
-    std::lock_guard<std::mutex> lock(g_mode_mutex);
+    std::lock_guard<std::recursive_mutex> lock(vb::state_mutex());
     static DevBuf space;
     vb::PoseMode& M = vb::global_pose_mode();
     if (int e = M.init()) return e;

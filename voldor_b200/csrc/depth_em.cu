@@ -842,6 +842,11 @@ int DepthEM::run(int N, int N_dp, const DepthHyper& hp, bool update_rigidness_on
     return 0;
 }
 
+std::recursive_mutex& state_mutex() {
+    static std::recursive_mutex m;
+    return m;
+}
+
 DepthEM& global_depth_em() {
     static DepthEM inst;
     return inst;

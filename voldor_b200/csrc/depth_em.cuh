@@ -5,6 +5,7 @@
 // One DepthEM instance per process/device keeps what the reference keeps in file statics, including the
 // per-pixel XORWOW streams that advance across calls and windows (optimize_depth.cu:357-361).
 #pragma once
+#include <mutex>
 #include "common.cuh"
 
 namespace vb {
@@ -67,6 +68,10 @@ struct DepthEM {
 };
 
 DepthEM& global_depth_em();
+
+// Guards the process-wide device state (DepthEM, Collector, PoseMode, hypothesis tables): every ABI entry point and
+// the window pipeline take it, so calls from different host threads serialise (the reference relies on the GIL).
+std::recursive_mutex& state_mutex();
 
 // Optional in-library timing of the dominant kernel (fused cost + random search), CUDA events on the launching
 // stream.  Off by default; bench.py switches it on for the roofline figure (vb_profile_* in voldor_b200.h).

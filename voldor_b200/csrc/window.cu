@@ -29,7 +29,6 @@ namespace vb {
 
 namespace {
 
-std::mutex g_window_mutex;
 
 struct Camera {  // reference: voldor/utils.h:30-76
     float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -533,7 +532,7 @@ int run_window(const float* flows_pt, const float* disparity_pt, const float* di
                float fx, float fy, float cx, float cy, float basefocal, int N, int N_dp, int w, int h,
                const char* config_pt, int* n_registered, float* poses_pt, float* poses_covar_pt, float* depth_pt,
                float* depth_conf_pt, int* iters_run, float* stats) {
-    std::lock_guard<std::mutex> lock(g_window_mutex);
+    std::lock_guard<std::recursive_mutex> lock(state_mutex());
     auto t0 = std::chrono::high_resolution_clock::now();
     Window W;
     W.cfg.fx = fx, W.cfg.cx = cx, W.cfg.fy = fy, W.cfg.cy = cy, W.cfg.basefocal = basefocal;
@@ -606,7 +605,7 @@ VB_EXPORT int vb_bootstrap_from_flow(const float* flow, int w, int h, const floa
 }
 
 VB_EXPORT int vb_set_bootstrap_override(int valid, const float* R9, const float* t3, const float* depth, int w, int h) {
-    std::lock_guard<std::mutex> lock(vb::g_window_mutex);
+    std::lock_guard<std::recursive_mutex> lock(vb::state_mutex());
     vb::g_bootstrap.valid = valid != 0;
     if (!valid) return 0;
     memcpy(vb::g_bootstrap.R, R9, 9 * sizeof(float));
