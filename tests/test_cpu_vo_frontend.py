@@ -1,0 +1,86 @@
+"""VO front-end (window chaining of voldor_slam.py:process_vo) with a stub window solver: no GPU needed."""
+import numpy as np
+
+import synth
+from voldor_b200 import formats, vo_frontend
+
+
+def _gt_poses6(win):
+    return np.stack([np.concatenate([vo_frontend.matrix_to_rvec(win["Rs"][i]), win["ts"][i]]) for i in range(win["N"])])
+
+
+def test_rvec_matrix_round_trip():
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        r = rng.normal(size=3) * rng.choice([1e-9, 0.01, 1.0, 3.0])
+        R = vo_frontend.rvec_to_matrix(r)
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-12)
+        assert np.allclose(vo_frontend.rvec_to_matrix(vo_frontend.matrix_to_rvec(R)), R, atol=1e-9)
+    # rotation by pi
+    R = vo_frontend.rvec_to_matrix(np.array([0, np.pi, 0]))
+    assert np.allclose(vo_frontend.rvec_to_matrix(vo_frontend.matrix_to_rvec(R)), R, atol=1e-6)
+
+
+def test_window_chaining_with_stub_solver():
+    F, w, h = 9, 64, 48
+    win = synth.make_window(w, h, F, seed=4)
+    gt = _gt_poses6(win)
+    calls = []
+
+    def stub(flows, fx, fy, cx, cy, basefocal=0, disparity=None, depth_priors=None, depth_prior_poses=None,
+             depth_prior_pconfs=None, config=""):
+        start = len(calls) and calls[-1]["next"]
+        n = flows.shape[0]
+        calls.append(dict(start=start, n=n, priors=None if depth_priors is None else depth_priors.shape[0],
+                          prior_poses=depth_prior_poses, config=config))
+        return {"n_registered": n, "poses": gt[start:start + n].astype(np.float32),
+                "poses_covar": np.zeros((n, 6, 6), np.float32), "depth": np.full((h, w), 8.0, np.float32),
+                "depth_conf": np.ones((h, w), np.float32)}
+
+    vo = vo_frontend.VisualOdometry(win["fx"], win["fy"], win["cx"], win["cy"], winsize=4, solver=stub)
+    orig_step = vo.step
+
+    def step(flows, disparity=None):
+        r = orig_step(flows, disparity)
+        calls[-1]["next"] = vo.fid_cur
+        return r
+
+    vo.step = step
+    Tcw = vo.run(list(win["flows"]))
+    assert len(Tcw) == F + 1
+    want = formats.accumulate_poses(gt)
+    for a, b in zip(Tcw, want):
+        assert np.allclose(a, b, atol=1e-6)
+    # first window has no prior, later ones hand over the temporal keyframe with its pose relative to the current frame
+    assert calls[0]["priors"] is None and calls[0]["config"].startswith("--silent --meanshift_kernel_var 0.2")
+    assert all(c["priors"] in (1, 2) for c in calls[1:])
+    c1 = calls[1]
+    T_rel = vo_frontend.T6_to_T44(c1["prior_poses"][0])
+    # keyframe = frame 0, current = frame calls[1]['start']: relative pose = inverse of the chained motion
+    T_chain = np.eye(4)
+    for i in range(c1["start"]):
+        T_chain = vo_frontend.T6_to_T44(gt[i]) @ T_chain
+    assert np.allclose(T_rel, np.linalg.inv(T_chain), atol=1e-5)
+
+
+def test_tracking_loss_restarts_without_priors():
+    F, w, h = 4, 32, 24
+    win = synth.make_window(w, h, F, seed=5)
+    gt = _gt_poses6(win)
+    state = {"k": 0, "priors": []}
+
+    def stub(flows, *a, depth_priors=None, **kw):
+        state["k"] += 1
+        state["priors"].append(depth_priors is not None)
+        if state["k"] == 2:
+            return {"n_registered": 0, "poses": np.zeros((0, 6), np.float32), "poses_covar": np.zeros((0, 6, 6)),
+                    "depth": np.zeros((h, w), np.float32), "depth_conf": np.zeros((h, w), np.float32)}
+        n = 1
+        return {"n_registered": n, "poses": gt[:n].astype(np.float32), "poses_covar": np.zeros((n, 6, 6), np.float32),
+                "depth": np.full((h, w), 8.0, np.float32), "depth_conf": np.ones((h, w), np.float32)}
+
+    vo = vo_frontend.VisualOdometry(win["fx"], win["fy"], win["cx"], win["cy"], winsize=1, solver=stub)
+    Tcw = vo.run(list(win["flows"]))
+    assert len(Tcw) == F + 1 and vo.lost == [1]
+    assert state["priors"] == [False, True, False, True]
+    assert np.allclose(Tcw[1], Tcw[2])  # the pose is kept across the lost frame

@@ -153,3 +153,52 @@ def test_baseline_config_shapes_bit_exact(name, w, h, N, iters, poses, kind):
     voldor_b200.set_bootstrap_override()
     assert ref["n_registered"] == N
     _compare(f"window {name} {w}x{h}x{N} resident-vs-ref", mine, ref)
+
+
+def test_vo_sequence_chained_windows_bit_exact():
+    """A 10-flow sequence through the VO front-end (sliding windows, keyframe depth priors, covisibility steps):
+    identical trajectories and identical per-window outputs from the product and from the reference kernels under
+    the reference orchestration — covers RNG persistence across windows and priors built from own outputs."""
+    from voldor_b200 import vo_frontend
+
+    w, h, F = 160, 120, 10
+    win = synth.make_window(w, h, F, seed=51)
+    boot = (win["Rs"][0], win["ts"][0], synth.noisy_depth(win, 0.05))
+    user = "--no_trunc_iters 1000 --n_poses_to_sample 2048 "
+    outs = {"ref": [], "mine": []}
+
+    def ref_solver(flows, fx, fy, cx, cy, **kw):
+        first = kw.get("depth_priors") is None
+        r = oracle_host.run_window("ref", flows, fx, fy, cx, cy, boot=boot if first else None, **kw)
+        outs["ref"].append(r)
+        return r
+
+    def my_solver(flows, fx, fy, cx, cy, **kw):
+        if kw.get("depth_priors") is None:
+            voldor_b200.set_bootstrap_override(*boot)
+        r = voldor_b200.voldor_ex(flows, fx, fy, cx, cy, **kw)
+        voldor_b200.set_bootstrap_override()
+        outs["mine"].append(r)
+        return r
+
+    ffi.libc_srand(31)
+    vo_ref = vo_frontend.VisualOdometry(win["fx"], win["fy"], win["cx"], win["cy"], winsize=4, user_config=user,
+                                        solver=ref_solver)
+    T_ref = vo_ref.run(list(win["flows"]))
+    ffi.libc_srand(31)
+    vo_mine = vo_frontend.VisualOdometry(win["fx"], win["fy"], win["cx"], win["cy"], winsize=4, user_config=user,
+                                         solver=my_solver)
+    T_mine = vo_mine.run(list(win["flows"]))
+    assert len(outs["ref"]) == len(outs["mine"]) >= 3
+    for k, (a, b) in enumerate(zip(outs["mine"], outs["ref"])):
+        _compare(f"vo sequence window {k}", a, b)
+    assert len(T_ref) == len(T_mine) == F + 1
+    for a, b in zip(T_mine, T_ref):
+        assert np.array_equal(a, b)
+    # and the trajectory is the ground truth up to the monocular scale
+    gt = np.stack([np.concatenate([vo_frontend.matrix_to_rvec(win["Rs"][i]), win["ts"][i]]) for i in range(F)])
+    T_gt = vo_frontend.formats.accumulate_poses(gt)
+    scale = np.linalg.norm(T_mine[-1][:3, 3]) / np.linalg.norm(T_gt[-1][:3, 3])
+    for a, b in zip(T_mine, T_gt):
+        assert np.abs(a[:3, :3] - b[:3, :3]).max() < 2e-2
+        assert np.linalg.norm(a[:3, 3] - b[:3, 3] * scale) < 0.1 * np.linalg.norm(T_mine[-1][:3, 3])

@@ -1,0 +1,174 @@
+"""Sliding-window visual odometry front-end: the caller side of the window solver ("callers").
+
+Behavioural source: the VO part of reference slam_py/voldor_slam.py `process_vo` (:417-536) — which windows are
+formed, which keyframe depths are handed over as priors and with which relative pose, how far the window start moves
+(covisibility, slam_utils.py:18-49) and how window poses are chained into the trajectory (:506-519).  Mapping, loop
+closure, frame alignment and pose-graph optimisation of the reference SLAM system are out of scope;
+this front-end is what is needed to turn a flow sequence into a trajectory with `voldor_b200.voldor`.
+
+numpy only (no OpenCV): rvec <-> matrix conversions are the Rodrigues formulas, `polish_T44` an SVD projection.
+"""
+import numpy as np
+
+from . import formats
+from .pyvoldor_vo import voldor
+
+
+def rvec_to_matrix(rvec):
+    rvec = np.asarray(rvec, np.float64)
+    th = np.linalg.norm(rvec)
+    if th < 1e-12:
+        return np.eye(3)
+    k = rvec / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+
+
+def matrix_to_rvec(R):
+    R = np.asarray(R, np.float64)
+    s = 0.5 * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])  # sin(theta) * axis
+    sn, c = np.linalg.norm(s), np.clip((np.trace(R) - 1) / 2, -1, 1)
+    th = np.arctan2(sn, c)
+    if sn > 1e-6:
+        return s * (th / sn)
+    if c > 0:  # theta -> 0: sin(theta)/theta -> 1
+        return s
+    A = (R + np.eye(3)) / 2  # theta -> pi: axis from the symmetric part
+    ax = np.sqrt(np.maximum(np.diag(A), 0))
+    i = int(np.argmax(ax))
+    ax = A[i] / ax[i]
+    return ax / np.linalg.norm(ax) * th
+
+
+def T6_to_T44(p):
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = rvec_to_matrix(p[:3]), p[3:6]
+    return T
+
+
+def T44_to_T6(T):
+    return np.concatenate([matrix_to_rvec(T[:3, :3]), T[:3, 3]])
+
+
+def polish_T44(T):
+    u, _, vt = np.linalg.svd(T[:3, :3])
+    T[:3, :3] = u @ vt
+
+
+def eval_covisibility(depth, Tc1c2, K, mask=None, stride=4):
+    """fraction of the (strided) pixels of a depth map that stay in view after Tc1c2 (slam_utils.py:18-49)"""
+    h, w = depth.shape
+    Iy, Ix = np.mgrid[0:h:stride, 0:w:stride]
+    rays = (np.linalg.inv(K) @ np.stack([Ix, Iy, np.ones_like(Ix)], 2).reshape(-1, 3).astype(np.float64).T).T
+    X = rays * depth[::stride, ::stride].reshape(-1, 1)
+    if mask is not None:
+        X = X[mask[::stride, ::stride].reshape(-1)]
+    X = X @ Tc1c2[:3, :3].T + Tc1c2[:3, 3]
+    p = X @ np.asarray(K, np.float64).T
+    p = p[p[:, 2] > 0]
+    p = p[:, :2] / p[:, 2:3]
+    vis = (p[:, 0] > 0) & (p[:, 0] < w) & (p[:, 1] > 0) & (p[:, 1] < h)
+    return vis.sum() / ((w // stride) * (h // stride))
+
+
+class VisualOdometry:
+    """Frame-to-frame trajectory from dense flows.  `flows[i]` maps frame i to frame i+1.
+
+    mode 'mono':   config as voldor_slam.py:149 (`--meanshift_kernel_var 0.2 --delta 1.5 --max_iters 5`)
+    mode 'stereo': needs `basefocal` and one disparity map per window start (voldor_slam.py:145)
+    """
+
+    def __init__(self, fx, fy, cx, cy, basefocal=0.0, mode="mono", winsize=5, user_config="", use_depth_priors=True,
+                 solver=voldor):
+        self.fx, self.fy, self.cx, self.cy, self.basefocal = fx, fy, cx, cy, basefocal
+        self.K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float64)
+        self.mode, self.winsize, self.use_depth_priors, self.solver = mode, winsize, use_depth_priors, solver
+        if mode == "stereo":
+            self.config = "--silent --meanshift_kernel_var 0.1 --disp_delta 1 --delta 0.2 --max_iters 4 "
+        else:
+            self.config = "--silent --meanshift_kernel_var 0.2 --delta 1.5 --max_iters 5 "
+        self.config += user_config
+        self.vostep_visibility_thresh = 0.8   # voldor_slam.py:88-90
+        self.spakf_visibility_thresh = 0.8
+        self.depth_covis_conf_thresh = 0.1
+        # state: world->current transform (the reference calls it Twc_cur), per-frame camera-to-world poses,
+        # keyframe depth maps
+        self.T_cur = np.eye(4)
+        self.Tcw = []          # list of 4x4, one per registered frame
+        self.kf_depth = {}     # fid -> (depth, depth_conf)
+        self.fid_cur, self.fid_tmpkf, self.fid_spakf = 0, -1, -1
+        self.lost = []
+
+    def _priors(self):
+        ids = []
+        if self.use_depth_priors:
+            if self.fid_tmpkf >= 0:
+                ids.append(self.fid_tmpkf)
+            if self.fid_spakf >= 0 and self.fid_spakf != self.fid_tmpkf:
+                ids.append(self.fid_spakf)
+        ids = [f for f in ids if f in self.kf_depth]
+        if not ids:
+            return None, None, None
+        dp = np.stack([self.kf_depth[f][0] for f in ids]).astype(np.float32)
+        pc = np.stack([self.kf_depth[f][1] for f in ids]).astype(np.float32)
+        # pose of the keyframe relative to the current frame (voldor_slam.py:440)
+        poses = np.stack([T44_to_T6(np.linalg.inv(self.T_cur @ self.Tcw[f])) for f in ids]).astype(np.float32)
+        return dp, pc, poses
+
+    def step(self, flows, disparity=None):
+        """solve one window starting at the current frame; returns the solver's dict (plus 'vo_step')"""
+        flows = np.ascontiguousarray(flows[: self.winsize], np.float32)
+        dp, pc, poses = self._priors()
+        r = self.solver(flows, self.fx, self.fy, self.cx, self.cy, basefocal=self.basefocal,
+                        disparity=disparity if self.mode == "stereo" else None, depth_priors=dp,
+                        depth_prior_pconfs=pc, depth_prior_poses=poses, config=self.config)
+        if r["n_registered"] == 0:
+            # tracking lost: keep the pose, restart without priors (voldor_slam.py:462-470)
+            self.lost.append(self.fid_cur)
+            self.Tcw.append(np.linalg.inv(self.T_cur))
+            self.fid_tmpkf = self.fid_spakf = -1
+            self.fid_cur += 1
+            r["vo_step"] = 1
+            return r
+        T = [T6_to_T44(p) for p in r["poses"]]
+        # how many frames to advance: while the window's depth map stays covisible (voldor_slam.py:496-504)
+        vo_step, T_tmp = 0, np.eye(4)
+        mask = r["depth_conf"] > self.depth_covis_conf_thresh
+        for i in range(r["n_registered"]):
+            vo_step += 1
+            T_tmp = T[i] @ T_tmp
+            if eval_covisibility(r["depth"], T_tmp, self.K, mask) < self.vostep_visibility_thresh:
+                break
+        for i in range(vo_step):
+            self.Tcw.append(np.linalg.inv(self.T_cur))
+            if i == 0:
+                self.kf_depth[self.fid_cur] = (r["depth"], r["depth_conf"])
+            self.T_cur = T[i] @ self.T_cur
+            polish_T44(self.T_cur)
+        # spatial keyframe: replaced when it is no longer covisible with the current frame (voldor_slam.py:521-531)
+        if self.fid_spakf >= 0 and self.fid_spakf in self.kf_depth:
+            d, c = self.kf_depth[self.fid_spakf]
+            T_spa2cur = self.T_cur @ self.Tcw[self.fid_spakf]
+            if eval_covisibility(d, T_spa2cur, self.K, c > self.depth_covis_conf_thresh) < self.spakf_visibility_thresh:
+                self.fid_spakf = self.fid_cur
+        else:
+            self.fid_spakf = self.fid_cur
+        self.fid_tmpkf = self.fid_cur
+        self.fid_cur += vo_step
+        # only the two live keyframes are needed again
+        for f in [k for k in self.kf_depth if k not in (self.fid_tmpkf, self.fid_spakf)]:
+            del self.kf_depth[f]
+        r["vo_step"] = vo_step
+        return r
+
+    def run(self, flows, disparities=None):
+        """whole sequence: flows [F,H,W,2] (or a list); returns the list of camera-to-world poses (F+1 of them)"""
+        n = len(flows)
+        while self.fid_cur < n:
+            window = np.stack(flows[self.fid_cur:self.fid_cur + self.winsize])
+            self.step(window, None if disparities is None else disparities[self.fid_cur])
+        self.Tcw.append(np.linalg.inv(self.T_cur))  # last frame (voldor_slam.py:420)
+        return self.Tcw
+
+    def save_poses(self, path, format="KITTI"):
+        formats.save_poses(path, self.Tcw, format)
