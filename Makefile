@@ -1,7 +1,7 @@
 # voldor_b200 build: sm_100a CUDA library (the product) + oracle (test infrastructure)
 NVCC ?= nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := -O3 $(ARCH) -lineinfo -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden,-O3
+NVFLAGS := -O3 $(ARCH) -lineinfo -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden,-O3,-ffp-contract=off
 CSRC := voldor_b200/csrc
 SRCS := $(wildcard $(CSRC)/*.cu)
 OBJS := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))

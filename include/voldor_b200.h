@@ -101,6 +101,10 @@ void vb_profile_counters(long long* out5);
  * VB_POSE_MODE_PHASES is set before the first call.  Returns 0, or 1 when not collected. */
 int vb_debug_pose_mode_phases(long long* out8);
 
+/* Test hook: rotation vector -> matrix through the device and the host instantiation of the same deterministic
+ * double-precision routine (csrc/host_math.h); the window pipeline relies on both giving identical bits. */
+int vb_debug_rvec_to_matrix(const float* rvecs, int n, float* R_device, float* R_host);
+
 /* Test hook for the speculative use of the libc rand() stream by the fused mean-shift start-sample selection
  * (csrc/libc_rand.h): snapshot, draw `draw` numbers, rewind, draw `keep`.  Afterwards the process-wide stream must
  * be exactly `keep` draws past where it was.  Returns 0, or 1 if the state array could not be captured. */

@@ -272,3 +272,24 @@ def test_align_frame_parity(libs, crw):
         scale = np.maximum(np.abs(b[fin]), 1e-3 * np.abs(b[fin]).max())
         assert (np.abs(a[fin] - b[fin]) / scale).max() <= 1e-4, rep
     assert np.isfinite(outs[1][0]).mean() > 0.5
+
+
+def test_rvec_to_matrix_identical_on_host_and_device():
+    """the pipelined camera loop converts poses on the device, the oracle orchestration on the host: same source,
+    every operation individually rounded, own sin/cos -> identical bits (csrc/host_math.h)"""
+    import ctypes as C
+    lib = C.CDLL(ffi.OURS)
+    rng = np.random.default_rng(0)
+    r = np.concatenate([rng.normal(0, s, (4000, 3)) for s in (1e-20, 1e-6, 0.01, 0.3, 1.5, 10.0)]).astype(np.float32)
+    r[0] = 0
+    n = r.shape[0]
+    Rd, Rh = np.zeros((n, 9), np.float32), np.zeros((n, 9), np.float32)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    assert lib.vb_debug_rvec_to_matrix(fp(r), n, fp(Rd), fp(Rh)) == 0
+    assert ffi.bits_equal(Rd, Rh)
+    # and it is a rotation by |r| about r
+    R = Rh.reshape(n, 3, 3).astype(np.float64)
+    assert np.abs(R @ R.transpose(0, 2, 1) - np.eye(3)).max() < 1e-6
+    k = 5000
+    want = synth.rodrigues(r[k].astype(np.float64))
+    assert np.abs(R[k] - want).max() < 1e-6

@@ -6,6 +6,7 @@
 #include "../../include/gpu_kernels.h"
 #include "../../include/voldor_b200.h"
 #include "depth_em.cuh"
+#include "host_math.h"
 #include "libc_rand.h"
 #include "pose_mode.cuh"
 #include "pose_sampler.cuh"
@@ -265,6 +266,24 @@ DLL_EXPORT int vb_debug_pose_mode_phases(long long* out8) {
     vb::PoseMode& M = vb::global_pose_mode();
     if (!M.d_phase_cycles) return 1;
     return (int)cudaMemcpy(out8, M.d_phase_cycles, 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+}
+// rvec -> R through the device code path and through the host code path of the same source (csrc/host_math.h)
+namespace {
+__global__ void k_debug_rvec_to_matrix(const float* rvecs, int n, float* R) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) vb::hm::rvec_to_matrix(rvecs + 3 * i, R + 9 * i);
+}
+}  // namespace
+DLL_EXPORT int vb_debug_rvec_to_matrix(const float* rvecs, int n, float* R_device, float* R_host) {
+    float *d_in = nullptr, *d_out = nullptr;
+    if (cudaMalloc((void**)&d_in, (size_t)n * 3 * sizeof(float)) != cudaSuccess) return 1;
+    if (cudaMalloc((void**)&d_out, (size_t)n * 9 * sizeof(float)) != cudaSuccess) return 1;
+    cudaMemcpy(d_in, rvecs, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice);
+    k_debug_rvec_to_matrix<<<(n + 127) / 128, 128>>>(d_in, n, d_out);
+    const cudaError_t e = cudaMemcpy(R_device, d_out, (size_t)n * 9 * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d_in), cudaFree(d_out);
+    for (int i = 0; i < n; i++) vb::hm::rvec_to_matrix(rvecs + 3 * i, R_host + 9 * i);
+    return (int)e;
 }
 DLL_EXPORT int vb_debug_rand_speculate(int draw, int keep) {
     vb::LibcRandSnapshot snap;

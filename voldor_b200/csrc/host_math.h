@@ -11,6 +11,12 @@
 #include <cmath>
 #include <cstring>
 
+#if defined(__CUDACC__)
+#define VB_HD __host__ __device__
+#else
+#define VB_HD
+#endif
+
 namespace vb {
 namespace hm {
 
@@ -19,20 +25,99 @@ inline void mat3_mul(const double* A, const double* B, double* C) {
         for (int j = 0; j < 3; j++) C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
 }
 
-// rvec (float[3]) -> R (float[9], row-major)
-inline void rvec_to_matrix(const float* rvec, float* R9) {
+// ---------------------------------------------------------------------------------------------------------
+// Deterministic double arithmetic shared by host and device code.  rvec -> R runs on the host (window set-up,
+// oracle orchestration) AND inside the mean-shift kernel (the pose of camera i feeds camera i+1 of the same EM
+// iteration without a host round trip), so it must give the same bits on both sides: every operation is an
+// individually rounded IEEE add/mul/div/sqrt (explicit *_rn intrinsics on the device, no FMA contraction on the
+// host: the translation units are built with -ffp-contract=off), and sin/cos are evaluated here instead of by
+// libm / libdevice.
+// ---------------------------------------------------------------------------------------------------------
+namespace det {
+VB_HD inline double mul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+VB_HD inline double add(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+VB_HD inline double sub(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+VB_HD inline double div(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+VB_HD inline double root(double a) {
+#if defined(__CUDA_ARCH__)
+    return __dsqrt_rn(a);
+#else
+    return std::sqrt(a);
+#endif
+}
+
+// sin and cos of x >= 0: Cody-Waite reduction by pi/2 (two-part constant), then the classic minimax kernels on
+// [-pi/4, pi/4] (coefficients of the freely distributable fdlibm k_sin.c / k_cos.c), Horner form.
+VB_HD inline void sincos(double x, double* s_out, double* c_out) {
+    const double n = floor(add(mul(x, 6.36619772367581382433e-01), 0.5));  // nearest multiple of pi/2
+    const double r = sub(sub(x, mul(n, 1.57079632673412561417e+00)), mul(n, 6.07710050650619224932e-11));
+    const double z = mul(r, r);
+    // sin(r)
+    double p = add(-2.50507602534068634195e-08, mul(z, 1.58969099521155010221e-10));
+    p = add(2.75573137070700676789e-06, mul(z, p));
+    p = add(-1.98412698298579493134e-04, mul(z, p));
+    p = add(8.33333333332248946124e-03, mul(z, p));
+    p = add(-1.66666666666666324348e-01, mul(z, p));
+    const double sr = add(r, mul(mul(z, r), p));
+    // cos(r)
+    double q = add(2.08757232129817482790e-09, mul(z, -1.13596475577881948265e-11));
+    q = add(-2.75573143513906633035e-07, mul(z, q));
+    q = add(2.48015872894767294178e-05, mul(z, q));
+    q = add(-1.38888888888741095749e-03, mul(z, q));
+    q = add(4.16666666666666019037e-02, mul(z, q));
+    const double cr = sub(1.0, sub(mul(0.5, z), mul(mul(z, z), q)));
+    const int quad = (int)(n - 4.0 * floor(n * 0.25));  // exact: n is a small non-negative integer
+    double s = sr, c = cr;
+    if (quad == 1) s = cr, c = -sr;
+    if (quad == 2) s = -sr, c = -cr;
+    if (quad == 3) s = -cr, c = sr;
+    *s_out = s, *c_out = c;
+}
+}  // namespace det
+
+// rvec (float[3]) -> R (float[9], row-major); host and device, bit-identical on both
+VB_HD inline void rvec_to_matrix(const float* rvec, float* R9) {
+    using namespace det;
     const double rx = rvec[0], ry = rvec[1], rz = rvec[2];
-    const double theta = std::sqrt(rx * rx + ry * ry + rz * rz);
+    const double theta = root(add(add(mul(rx, rx), mul(ry, ry)), mul(rz, rz)));
     double R[9];
     if (theta < 2.220446049250313e-16) {
         R[0] = 1, R[1] = 0, R[2] = 0, R[3] = 0, R[4] = 1, R[5] = 0, R[6] = 0, R[7] = 0, R[8] = 1;
     } else {
-        const double c = std::cos(theta), s = std::sin(theta), c1 = 1. - c;
-        const double itheta = 1. / theta;
-        const double x = rx * itheta, y = ry * itheta, z = rz * itheta;
-        R[0] = c + c1 * x * x, R[1] = c1 * x * y - s * z, R[2] = c1 * x * z + s * y;
-        R[3] = c1 * x * y + s * z, R[4] = c + c1 * y * y, R[5] = c1 * y * z - s * x;
-        R[6] = c1 * x * z - s * y, R[7] = c1 * y * z + s * x, R[8] = c + c1 * z * z;
+        double s, c;
+        sincos(theta, &s, &c);
+        const double c1 = sub(1., c);
+        const double itheta = div(1., theta);
+        const double x = mul(rx, itheta), y = mul(ry, itheta), z = mul(rz, itheta);
+        const double c1x = mul(c1, x), c1y = mul(c1, y), c1z = mul(c1, z);
+        const double sx = mul(s, x), sy = mul(s, y), sz = mul(s, z);
+        R[0] = add(c, mul(c1x, x)), R[1] = sub(mul(c1x, y), sz), R[2] = add(mul(c1x, z), sy);
+        R[3] = add(mul(c1x, y), sz), R[4] = add(c, mul(c1y, y)), R[5] = sub(mul(c1y, z), sx);
+        R[6] = sub(mul(c1x, z), sy), R[7] = add(mul(c1y, z), sx), R[8] = add(c, mul(c1z, z));
     }
     for (int i = 0; i < 9; i++) R9[i] = (float)R[i];
 }

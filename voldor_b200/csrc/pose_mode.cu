@@ -14,6 +14,7 @@
 #include "residual_model.cuh"
 #include "tree_sum.cuh"
 #include "libc_rand.h"
+#include "host_math.h"
 #include <cmath>
 #include <cooperative_groups.h>
 #include <cstdlib>
@@ -61,7 +62,28 @@ struct MeanshiftArgs {
     int trial_idx[kMaxTrialBatch];
     float good_init_confidence;
     PoolSource src;
+    PoseTail tail;
 };
+
+// camera pose from the mean-shift mode (reference voldor/geometry.cpp:247-262 for a successive pose without robust
+// refinement); mirrors Window::apply_camera_result on the host
+__device__ void pose_tail(const PoseTail& T, const float* mode, int dims, int n_points, int pool_used,
+                          MeanshiftResult* out) {
+    int ok = (n_points >= 4 && pool_used > 0 && dims == 6) ? 1 : 0;
+    float pose[6] = {0, 0, 0, 0, 0, 0};
+    if (ok) {
+        for (int d = 0; d < 6; d++) pose[d] = mode[d];
+        for (int d = 0; d < 3; d++) pose[d] = f_mul(pose[d], T.inv_rvec_scale);
+        for (int d = 0; d < 6; d++)
+            if (!isfinite(pose[d])) ok = 0;  // cv::checkRange
+    }
+    out->ok = ok;
+    if (!ok) return;
+    float R[9];
+    hm::rvec_to_matrix(pose, R);
+    for (int k = 0; k < 9; k++) out->R[k] = R[k], T.d_cams->R[T.cam_index][k] = R[k];
+    for (int k = 0; k < 3; k++) out->t[k] = pose[3 + k], T.d_cams->t[T.cam_index][k] = pose[3 + k];
+}
 
 // Ordered compaction of finite hypotheses across the whole cluster; returns the pool size on every thread.
 __device__ int build_pool(const PoolSource& S, cg::cluster_group& cluster, int rank) {
@@ -228,6 +250,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
         if (rank == 0 && threadIdx.x == 0) {
             out->used_iters = 0, out->n = N, out->weight_sum = 0.f, out->confidence = 0.f;
             out->aux_count = A.src.aux_count ? *A.src.aux_count : 0;
+            out->ok = 0;
         }
         return;
     }
@@ -368,6 +391,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
         out->trials_used = s_trials_used;
         out->aux_count = A.src.aux_count ? *A.src.aux_count : 0;
         out->n = N;
+        if (A.tail.d_cams) pose_tail(A.tail, io_mean, dims, out->aux_count, N, out);
     }
 }
 
@@ -680,8 +704,8 @@ void smem_plan(int n, int dims, int& slice_in_smem, size_t& bytes, int* centred_
 int PoseMode::init() {
     if (stream) return 0;
     VB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    VB_CUDA(cudaMalloc((void**)&d_result, sizeof(MeanshiftResult)));
-    VB_CUDA(cudaMallocHost((void**)&h_result, sizeof(MeanshiftResult)));
+    VB_CUDA(cudaMalloc((void**)&d_result, kMaxFrames * sizeof(MeanshiftResult)));
+    VB_CUDA(cudaMallocHost((void**)&h_result, kMaxFrames * sizeof(MeanshiftResult)));
     VB_CUDA(cudaMalloc((void**)&d_partials, (size_t)64 * kMaxTreeBlocks * sizeof(float)));
     VB_CUDA(cudaMalloc((void**)&d_rg_sums, 256 + kCluster * sizeof(int)));
     VB_CUDA(cudaMallocHost((void**)&h_rg_sums, 256));
@@ -800,6 +824,42 @@ int PoseMode::meanshift_from_hypotheses(const float* d_rvecs, const float* d_tve
     A.src.aux_count = d_aux_count;
     if (used_iters) *used_iters = 0;
     return run_meanshift(*this, A, n_poses, h_io_mean, h_o_confidence, used_iters);
+}
+
+int PoseMode::enqueue_from_hypotheses(int slot, const float* d_rvecs, const float* d_tvecs, int n_poses,
+                                      float rvec_scale, float* d_pool, int* d_used, int dims, float kernel_var,
+                                      const float* h_init_mean, float epsilon, int max_iters,
+                                      const int* d_aux_count, const PoseTail& tail) {
+    if (int e = init()) return e;
+    if (slot < 0 || slot >= kMaxFrames || n_poses > 512 * 512) return (int)cudaErrorInvalidValue;
+    MeanshiftArgs A;
+    memset(&A, 0, sizeof(A));
+    for (int d = 0; d < dims; d++) A.io_mean[d] = h_init_mean[d];
+    A.dims = dims, A.kernel_var = kernel_var, A.epsilon = epsilon, A.max_iters = max_iters;
+    A.center_idx = -1, A.trial_only = 0;
+    A.src.rvecs = d_rvecs, A.src.tvecs = d_tvecs, A.src.n_poses = n_poses, A.src.rvec_scale = rvec_scale;
+    A.src.pool_out = d_pool, A.src.used_out = d_used;
+    A.src.aux_count = d_aux_count;
+    A.src.cta_counts = (int*)((char*)d_rg_sums + 256);
+    A.tail = tail;
+    size_t smem_bytes;
+    bool fast6;
+    smem_plan(n_poses, dims, A.slice_in_smem, smem_bytes, nullptr, dims + 1, fast6);
+    if (fast6)
+        k_meanshift<true><<<kCluster, kThreads, smem_bytes, stream>>>(A, d_partials, d_result + slot);
+    else
+        k_meanshift<false><<<kCluster, kThreads, smem_bytes, stream>>>(A, d_partials, d_result + slot);
+    VB_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+int PoseMode::fetch_results(int n_slots) {
+    if (n_slots <= 0) return 0;
+    VB_CUDA(cudaMemcpyAsync(h_result, d_result, (size_t)n_slots * sizeof(MeanshiftResult), cudaMemcpyDeviceToHost, stream));
+    VB_CUDA(cudaStreamSynchronize(stream));
+    KernelProfile& prof = kernel_profile();
+    for (int i = 0; i < n_slots; i++) prof.meanshift_runs++, prof.meanshift_iters += h_result[i].used_iters;
+    return 0;
 }
 
 int PoseMode::fit_robust_gaussian(const float* d_space, int N, int dims, float scale, float* h_io_mean,

@@ -21,11 +21,24 @@ struct MeanshiftResult {
     int n;             // pool size seen by the kernel
     int aux_count;     // echo of the caller's device counter (number of P3P instances in the window pipeline)
     int trials_used;   // start-sample trials the reference's selection loop would have run (fused trial mode)
+    // pose tail (window pipeline, see PoseTail): camera pose derived from the mode on the device
+    int ok;
+    float R[9], t[3];
+};
+
+// Optional tail of the mean-shift launch in the window pipeline: turn the mode into the camera's rotation matrix and
+// translation ON THE DEVICE (reference voldor/geometry.cpp:191-262: un-scale the rotation vector, finite check,
+// Rodrigues) and store it in the device-resident camera block, so the next camera's kernels of the same EM
+// iteration can be enqueued without waiting for the host.
+struct PoseTail {
+    CamBlock* d_cams;
+    int cam_index;
+    float inv_rvec_scale;
 };
 
 struct PoseMode {
     cudaStream_t stream = nullptr;
-    MeanshiftResult* d_result = nullptr;  // device
+    MeanshiftResult* d_result = nullptr;  // device, kMaxFrames slots (slot 0 is the synchronous API's)
     MeanshiftResult* h_result = nullptr;  // pinned host mirror
     float* d_partials = nullptr;
     // robust fit scratch
@@ -48,6 +61,12 @@ struct PoseMode {
                                   float* d_pool, int* d_used, int dims, float kernel_var, float* h_io_mean,
                                   float* h_o_confidence, int* used_iters, float epsilon, int max_iters,
                                   const int* d_aux_count = nullptr);
+    // Asynchronous variant for the window pipeline: enqueue only, result (incl. the pose tail) goes to slot `slot`;
+    // fetch_results(n) copies slots [0,n) back and synchronises once.
+    int enqueue_from_hypotheses(int slot, const float* d_rvecs, const float* d_tvecs, int n_poses, float rvec_scale,
+                                float* d_pool, int* d_used, int dims, float kernel_var, const float* h_init_mean,
+                                float epsilon, int max_iters, const int* d_aux_count, const PoseTail& tail);
+    int fetch_results(int n_slots);
     // Robust Gaussian fit on x = scale * d_space (scale folds the caller's pose scaling).
     int fit_robust_gaussian(const float* d_space, int N, int dims, float scale, float* h_io_mean,
                             float* h_io_covar, float trunc_sigma, float covar_reg_lambda, float* h_o_density,

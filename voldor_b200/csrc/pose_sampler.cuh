@@ -30,6 +30,7 @@ struct Collector {
     const float* depth = nullptr;
     int depth_pitch = 0;
     CamBlock cam;
+    const CamBlock* d_cam = nullptr;  // when set, the compacting kernel reads the poses from device memory instead
 
     float* p2_map = nullptr;  // [h*w][2]  NaN where invalid
     float* p3_map = nullptr;  // [h*w][3]

@@ -21,6 +21,7 @@
 #include "pose_sampler.cuh"
 #include "residual_model.cuh"
 #include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <mutex>
 #include <vector>
@@ -148,6 +149,8 @@ struct Window {
         size_t out_cap = 0;
         float* d_disp = nullptr;
         size_t disp_cap = 0;
+        CamBlock* d_cams = nullptr;  // device-resident poses of the pipelined camera loop
+        CamBlock* h_cams = nullptr;  // pinned staging
     };
     static Scratch& scratch() {
         static Scratch sc;
@@ -172,6 +175,8 @@ struct Window {
             VB_CUDA(cudaMalloc((void**)&sc.sums, (kMaxFrames + kMaxPriorFrames) * sizeof(double)));
             VB_CUDA(cudaMallocHost((void**)&sc.h_sums, (kMaxFrames + kMaxPriorFrames) * sizeof(double)));
             VB_CUDA(cudaMallocHost((void**)&sc.h_counts, 4 * sizeof(int)));
+            VB_CUDA(cudaMalloc((void**)&sc.d_cams, sizeof(CamBlock)));
+            VB_CUDA(cudaMallocHost((void**)&sc.h_cams, sizeof(CamBlock)));
         }
         const size_t npx = (size_t)w * h;
         if (npx > sc.out_cap) {
@@ -424,10 +429,94 @@ struct Window {
     }
 
     // reference voldor.cpp:164-201
+    // The camera loop of one EM iteration without a host round trip per camera (reference voldor.cpp:170-195 +
+    // geometry.cpp:5-265, successive poses, no robust refinement): the kernels of all cameras are enqueued back to
+    // back; the mean-shift launch of camera i derives its R,t on the device (PoseTail) and stores them in the
+    // device-resident camera block the next camera's collection kernel reads.  One copy + one synchronisation per
+    // iteration; the host then replays the reference's sequential bookkeeping (failure / truncation) on the
+    // results, discarding what was computed past a truncation point.
+    int optimize_cameras_pipelined(bool allow_trunc) {
+        Scratch& sc = scratch();
+        for (int f = 0; f < n_flows; f++) {
+            memcpy(C.cam.R[f], cams[f].R, 9 * sizeof(float));
+            memcpy(C.cam.t[f], cams[f].t, 3 * sizeof(float));
+        }
+        *sc.h_cams = C.cam;
+        VB_CUDA(cudaMemcpyAsync(sc.d_cams, sc.h_cams, sizeof(CamBlock), cudaMemcpyHostToDevice, s));
+        dim3 g, b;
+        launch2d(g, b);
+        k_scale_copy<<<g, b, 0, s>>>(C.depth_own.ptr, C.depth_own.pitch, E.depth.ptr, E.depth.pitch, w, h,
+                                     depth_scale_pending);
+        C.stream = s, M.stream = s;
+        C.d_cam = sc.d_cams;
+        int planned = n_flows;  // cameras to attempt; a camera skipped by the density gate truncates right there
+        for (int i = 0; i < n_flows; i++) {
+            if (allow_trunc && !(cams[i].pose_rigidness_density > cfg.trunc_rigidness_density)) {
+                planned = i;
+                break;
+            }
+            CollectParams P;
+            P.active_idx = i, P.rigidness_thresh = cfg.rigidness_threshold;
+            P.rigidness_sum_thresh = cfg.rigidness_sum_threshold;
+            P.sample_min_depth = cfg.pose_sample_min_depth, P.sample_max_depth = cfg.pose_sample_max_depth;
+            P.max_trace_on_flow = cfg.max_trace_on_flow;
+            int e = C.collect(n_flows, P, true);
+            if (!e)
+                e = solve_batch_p3p_device(C.p3c, C.p2c, C.d_count, 0, K[0], K[4], K[2], K[5], sc.rvecs, sc.tvecs,
+                                           cfg.n_poses_to_sample, !cfg.lambdatwist, s);
+            float pose_opm[6];
+            hm::matrix_to_rvec(cams[i].R, pose_opm);
+            pose_opm[3] = cams[i].t[0], pose_opm[4] = cams[i].t[1], pose_opm[5] = cams[i].t[2];
+            for (int d = 0; d < 3; d++) pose_opm[d] *= cfg.meanshift_rvec_scale;
+            PoseTail tail;
+            tail.d_cams = sc.d_cams, tail.cam_index = i;
+            tail.inv_rvec_scale = (float)(1. / (double)cfg.meanshift_rvec_scale);
+            if (!e)
+                e = M.enqueue_from_hypotheses(i, sc.rvecs, sc.tvecs, cfg.n_poses_to_sample, cfg.meanshift_rvec_scale,
+                                              sc.pool, sc.d_used, 6, cfg.meanshift_kernel_var, pose_opm,
+                                              cfg.meanshift_epsilon, cfg.meanshift_max_iters, C.d_count, tail);
+            if (e) {
+                C.d_cam = nullptr;
+                return -1;
+            }
+        }
+        C.d_cam = nullptr;
+        if (M.fetch_results(planned)) return -1;
+        for (int i = 0; i < n_flows; i++) {
+            int ok = 0;
+            Camera& cam = cams[i];
+            if (i < planned) {
+                const MeanshiftResult& r = M.h_result[i];
+                if (r.aux_count >= 4 && r.n > 0) {
+                    if (r.used_iters > 0) cam.pose_density = r.confidence;
+                    cam.last_used_ms_iters = r.used_iters;
+                    cam.pose_sample_count = r.n;
+                    if (r.ok) {
+                        memcpy(cam.R, r.R, sizeof(cam.R));
+                        memcpy(cam.t, r.t, sizeof(cam.t));
+                        ok = 1;
+                    }
+                }
+            }
+            if (!ok || (allow_trunc && cam.pose_density < cfg.trunc_sample_density)) {
+                iters_remain = std::max(iters_remain, cfg.min_iters_after_trunc);
+                n_flows = i;
+                break;
+            }
+        }
+        return 0;
+    }
+
     int optimize_cameras() {
         const bool allow_trunc = iters_cur > cfg.no_trunc_iters;
         if (allow_trunc)
             if (int e = fetch_rigidness_densities()) return e;
+        // pipelined loop when every camera continues from its previous pose and no robust refinement is due
+        static const bool pipeline_off = getenv("VB_NO_CAMERA_PIPELINE") != nullptr;
+        bool pipelined = !pipeline_off && n_flows > 0 &&
+                         !(cfg.rg_refine && (!cfg.rg_refine_last_only || iters_remain == 0));
+        for (int i = 0; i < n_flows && pipelined; i++) pipelined = cams[i].pose_sample_count != 0;
+        if (pipelined) return optimize_cameras_pipelined(allow_trunc);
         for (int i = 0; i < n_flows; i++) {
             int ok = 0;
             if (!allow_trunc || cams[i].pose_rigidness_density > cfg.trunc_rigidness_density) {
