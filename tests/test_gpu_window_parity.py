@@ -202,3 +202,64 @@ def test_vo_sequence_chained_windows_bit_exact():
     for a, b in zip(T_mine, T_gt):
         assert np.abs(a[:3, :3] - b[:3, :3]).max() < 2e-2
         assert np.linalg.norm(a[:3, 3] - b[:3, 3] * scale) < 0.1 * np.linalg.norm(T_mine[-1][:3, 3])
+
+
+@pytest.mark.parametrize("flags", [
+    "--lambdatwist 0",
+    "--fb_smooth 0",
+    "--optimize_depth 0",
+    "--rg_refine_last_only 0",
+    "--rg_refine 0",
+    "--meanshift_max_init_trials 40",
+    "--meanshift_max_init_trials 1 --meanshift_good_init_confidence 0.0001",
+    "--norm_world_scale 0",
+    "--depth_rand_samples 3 --depth_global_prop_step 1 --depth_local_prop_width 8",
+    "--depth_global_prop_step 0 --depth_local_prop_width 0",
+    "--no_trunc_iters 1 --trunc_rigidness_density 0.93",
+    "--no_trunc_iters 1 --trunc_sample_density 0.02",
+    "--exclusive_gpu_context 0",
+    "--max_trace_on_flow 1 --rigidness_threshold 0.8",
+    "--abs_resize_factor 0.5 --lambda 0.2 --meanshift_kernel_var 0.2",
+    "--pose_sample_min_depth 6 --pose_sample_max_depth 9",
+    "--meanshift_max_iters 3 --rg_max_iters 4",
+])
+def test_mono_window_flag_variants_bit_exact(flags):
+    """configuration flags that switch code paths (solver, smoothing, truncation, start-sample fallbacks, ...)"""
+    w, h, N, iters = 112, 80, 4, 4
+    win, boot, _ = _mono_case(w, h, N, iters, seed=61)
+    cfg = f"--silent --max_iters {iters} --n_poses_to_sample 1536 {flags}"
+    args = (win["flows"], win["fx"], win["fy"], win["cx"], win["cy"])
+    libc = __import__("ctypes").CDLL(None)
+    ffi.libc_srand(90)
+    ref = oracle_host.run_window("ref", *args, config=cfg, boot=boot)
+    next_ref = libc.rand()
+    voldor_b200.set_bootstrap_override(*boot)
+    ffi.libc_srand(90)
+    mine = voldor_b200.voldor_ex(*args, config=cfg)
+    next_mine = libc.rand()
+    voldor_b200.set_bootstrap_override()
+    _compare(f"window flags [{flags}]", mine, ref)
+    # both sides must also have consumed the same number of libc rand() draws
+    assert next_mine == next_ref
+
+
+def test_mono_window_with_nonfinite_flow_pixels_bit_exact():
+    """NaN / inf in the input flows (failed optical-flow regions): every kernel must degrade exactly like the
+    reference's (NaN through the bilinear fetch, fmaxf/fminf clamps, strict comparisons)"""
+    w, h, N, iters = 112, 80, 4, 3
+    win, boot, _ = _mono_case(w, h, N, iters, seed=71)
+    flows = win["flows"].copy()
+    flows[0, 10:15, 20:26, :] = np.nan
+    flows[1, 40, 50, 0] = np.inf
+    flows[2, 60:62, 70:75, 1] = -np.inf
+    flows[3, 5, 5, :] = 1e30
+    cfg = f"--silent --max_iters {iters} --no_trunc_iters 1000 --n_poses_to_sample 1536"
+    args = (flows, win["fx"], win["fy"], win["cx"], win["cy"])
+    ffi.libc_srand(91)
+    ref = oracle_host.run_window("ref", *args, config=cfg, boot=boot)
+    voldor_b200.set_bootstrap_override(*boot)
+    ffi.libc_srand(91)
+    mine = voldor_b200.voldor_ex(*args, config=cfg)
+    voldor_b200.set_bootstrap_override()
+    assert ref["n_registered"] >= 1  # the reference itself drops the cameras whose pose pool is poisoned
+    _compare("window mono with non-finite flow pixels", mine, ref)

@@ -598,18 +598,38 @@ struct Window {
         dim3 g, b;
         launch2d(g, b);
         const size_t npx = (size_t)w * h;
+        // A window that lost every camera ends with 0/0 factors (world scale, 1/(n_flows+n_priors)).  The reference
+        // applies them on the host, where x86 produces the default NaN 0xFFC00000 while the GPU would produce
+        // 0x7FFFFFFF; those degenerate maps are finished on the host so that even the failure outputs match.
         if (depth_pt) {
-            k_scale_copy<<<g, b, 0, s>>>(sc.d_out, w, E.depth.ptr, E.depth.pitch, w, h, depth_scale_pending);
-            VB_CUDA(cudaMemcpyAsync(depth_pt, sc.d_out, npx * sizeof(float), cudaMemcpyDefault, s));
-            VB_CUDA(cudaStreamSynchronize(s));
+            if (std::isfinite(depth_scale_pending)) {
+                k_scale_copy<<<g, b, 0, s>>>(sc.d_out, w, E.depth.ptr, E.depth.pitch, w, h, depth_scale_pending);
+                VB_CUDA(cudaMemcpyAsync(depth_pt, sc.d_out, npx * sizeof(float), cudaMemcpyDefault, s));
+                VB_CUDA(cudaStreamSynchronize(s));
+            } else {
+                std::vector<float> raw(npx);
+                VB_CUDA(cudaMemcpy2DAsync(raw.data(), (size_t)w * sizeof(float), E.depth.ptr,
+                                          (size_t)E.depth.pitch * sizeof(float), (size_t)w * sizeof(float), h,
+                                          cudaMemcpyDeviceToHost, s));
+                VB_CUDA(cudaStreamSynchronize(s));
+                volatile float scale = depth_scale_pending;
+                for (size_t k = 0; k < npx; k++) raw[k] = raw[k] * scale;
+                VB_CUDA(cudaMemcpy(depth_pt, raw.data(), npx * sizeof(float), cudaMemcpyDefault));
+            }
         }
         if (depth_conf_pt) {
-            const int cp = (int)(E.dp_conf.pitch / sizeof(float));
             const float inv_n = (float)(1. / (double)(float)(n_flows + n_depth_priors));
-            k_depth_conf<<<g, b, 0, s>>>(sc.d_out, w, h, E.rig.ptr, E.rig.pitch, E.rig.layer_elems(), n_flows,
-                                         E.dp_conf.ptr, cp, (size_t)cp * h, n_depth_priors, inv_n);
-            VB_CUDA(cudaMemcpyAsync(depth_conf_pt, sc.d_out, npx * sizeof(float), cudaMemcpyDefault, s));
-            VB_CUDA(cudaStreamSynchronize(s));
+            if (n_flows + n_depth_priors > 0) {
+                const int cp = (int)(E.dp_conf.pitch / sizeof(float));
+                k_depth_conf<<<g, b, 0, s>>>(sc.d_out, w, h, E.rig.ptr, E.rig.pitch, E.rig.layer_elems(), n_flows,
+                                             E.dp_conf.ptr, cp, (size_t)cp * h, n_depth_priors, inv_n);
+                VB_CUDA(cudaMemcpyAsync(depth_conf_pt, sc.d_out, npx * sizeof(float), cudaMemcpyDefault, s));
+                VB_CUDA(cudaStreamSynchronize(s));
+            } else {
+                volatile float zero = 0.f, f = inv_n;
+                std::vector<float> conf(npx, zero * f);
+                VB_CUDA(cudaMemcpy(depth_conf_pt, conf.data(), npx * sizeof(float), cudaMemcpyDefault));
+            }
         }
         VB_RETURN_IF_CUDA_ERROR();
         return 0;
