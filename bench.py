@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — VOLDOR EM hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|cpu-port]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|cpu-port|abi-dropin]
 
 One "step" = one VO window (one pass of the hot path over one batch of synthetic input): BASELINE.json
 configs[1] — a single 640x480 frame with 8 flows, 30 EM iterations, monocular (bootstrap pose/depth
@@ -23,7 +23,8 @@ iterations per second, whole job (all ranks).  With N > 1 each rank runs its own
 files rebuilt for sm_100a) driven by the reference's host orchestration restated OpenCV-free over the ABI
 (oracle/host_voldor.cpp) — i.e. voldor.cpp's geometry loop on the host cores calling its gpu-kernels
 library, which is the only implementation of this path the reference has (there is no CPU E/M
-step in the reference).  --impl cpu-port times the CPU port instead.
+step in the reference).  --impl cpu-port times the CPU port instead; --impl abi-dropin times the same reference
+host orchestration over THIS library's gpu_kernels.h entry points (what a maintainer gets by only re-linking).
 """
 import argparse
 import ctypes as C
@@ -140,8 +141,9 @@ def bench_reference(args, rank, world):
             ffi.libc_srand(1000 + i)
             torch.cuda.synchronize()
             t0 = time.time()
-            r = oracle_host.run_window("ref", win["flows"], win["fx"], win["fy"], win["cx"], win["cy"], config=CONFIG,
-                                       boot=boot)
+            backend = "ours_abi" if args.impl == "abi-dropin" else "ref"
+            r = oracle_host.run_window(backend, win["flows"], win["fx"], win["fy"], win["cx"], win["cy"],
+                                       config=CONFIG, boot=boot)
             torch.cuda.synchronize()
             if i >= args.warmup:
                 times.append(time.time() - t0)
@@ -149,23 +151,28 @@ def bench_reference(args, rank, world):
         total = sum(times)
         value = iters / total
         kind = "reference"
+        if args.impl == "abi-dropin":
+            kind = "abi-dropin"
         sample = (f"full workload: {args.steps} windows of {W}x{H}x{NFLOWS}, {EM_ITERS} EM iterations each; reference "
                   "CUDA kernels (its own .cu files rebuilt for sm_100a, oracle/_ref) on 1 B200 driven by the reference "
                   "host orchestration (voldor.cpp/geometry.cpp restated OpenCV-free) on 1 host thread")
+        if args.impl == "abi-dropin":
+            sample = sample.replace("reference CUDA kernels (its own .cu files rebuilt for sm_100a, oracle/_ref)",
+                                    "voldor_b200's gpu_kernels.h entry points (library-level drop-in, host buffers)")
         ms_per_step = 1e3 * total / max(1, args.steps)
         clk = clocks.stop()
     line = {
-        "impl": "reference", "metric": "EM-iters/sec", "value": value, "unit": "EM-iterations/s", "n_gpus": args.gpus,
+        "impl": "reference" if args.impl != "abi-dropin" else "abi-dropin", "metric": "EM-iters/sec", "value": value, "unit": "EM-iterations/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"BASELINE configs[1]: single {W}x{H} frame, {NFLOWS} flows, {EM_ITERS} EM iters, "
                                f"monocular, {NPOSES} hypotheses/camera", "parallelism": "single window (rank 0)"},
-        "cpu_baseline": {"value": value, "unit": "EM-iterations/s", "cores": 1 if kind == "reference" else cores,
+        "cpu_baseline": {"value": value, "unit": "EM-iterations/s", "cores": 1 if kind != "port" else cores,
                          "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "EM-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "frames_per_sec": value * NFLOWS / EM_ITERS,
     }
-    if kind == "reference":
+    if kind != "port":
         line["clocks"] = clk
     print(json.dumps(line))
 
@@ -329,7 +336,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu-port"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu-port", "abi-dropin"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
