@@ -125,7 +125,7 @@ __device__ __forceinline__ unsigned long long scan_pack(unsigned epoch, unsigned
 }
 enum { SCAN_AGGREGATE = 1, SCAN_INCLUSIVE = 2 };
 
-template <int TILE>
+template <int TILE, bool CAM_IN_MEMORY>
 __global__ void __launch_bounds__(TILE)
     k_collect_compact(const CollectView A, const __grid_constant__ CamBlock Cparam, const CamBlock* __restrict__ d_cam,
                       const CollectParams P, ScanState S, float* p2c, float* p3c, int* total) {
@@ -135,13 +135,13 @@ __global__ void __launch_bounds__(TILE)
     // poses either by value (kernel parameter) or from device memory: inside an EM iteration the mean-shift kernel
     // of camera i-1 writes the pose this launch needs, without a host round trip
     __shared__ CamBlock s_cam;
-    if (d_cam) {
+    if (CAM_IN_MEMORY) {
         for (int k = threadIdx.x; k < (int)(sizeof(CamBlock) / sizeof(float)); k += TILE)
             reinterpret_cast<float*>(&s_cam)[k] = reinterpret_cast<const float*>(d_cam)[k];
     }
     if (threadIdx.x == 0) s_tile = atomicAdd(S.ticket, 1u) - S.ticket_base;
     __syncthreads();
-    const CamBlock& C = d_cam ? s_cam : Cparam;
+    const CamBlock& C = CAM_IN_MEMORY ? s_cam : Cparam;  // one address space per instantiation
     const unsigned tile = s_tile;
     const int npx = A.w * A.h;
     const int i = (int)tile * TILE + threadIdx.x;
@@ -342,7 +342,10 @@ int Collector::collect(int N, const CollectParams& P, bool compact) {
         if (scan_epoch >= (1u << 30)) scan_epoch = 0;  // descriptors hold 30 epoch bits; 0 is never issued
         const int nt = VB_DIV_CEIL(npx, kCompactTile);
         ticket_total += (unsigned)nt;
-        k_collect_compact<kCompactTile><<<nt, kCompactTile, 0, stream>>>(A, cam, d_cam, P, S, p2c, p3c, d_count);
+        if (d_cam)
+            k_collect_compact<kCompactTile, true><<<nt, kCompactTile, 0, stream>>>(A, cam, d_cam, P, S, p2c, p3c, d_count);
+        else
+            k_collect_compact<kCompactTile, false><<<nt, kCompactTile, 0, stream>>>(A, cam, d_cam, P, S, p2c, p3c, d_count);
     } else {
         k_collect<<<nb, kBlock, 0, stream>>>(A, cam, P);
     }
