@@ -96,10 +96,11 @@ void vb_profile_get(double* search_ms, long long* search_launches);
  * out5 = { mean-shift runs, their iterations, start-sample trials, robust-fit runs, their iterations }. */
 void vb_profile_counters(long long* out5);
 
-/* Profiling hook: per-phase clock64 totals of the robust-fit kernel (LU, E-step, level-1 sums, exchange barrier,
- * level-2 sums, M-step) accumulated since process start; only collected when the environment variable
- * VB_POSE_MODE_PHASES is set before the first call.  Returns 0, or 1 when not collected. */
-int vb_debug_pose_mode_phases(long long* out8);
+/* Profiling hook: per-phase clock64 totals accumulated since process start, only collected when the environment
+ * variable VB_POSE_MODE_PHASES is set before the first call.  out16[0..5]: robust fit (LU, E-step, level-1 sums,
+ * exchange barrier, level-2 sums, M-step); out16[8..15]: mean-shift (pool build, staging, weights, level-1 sums,
+ * exchange barrier, level-2 sums, mean update, result + pose tail).  Returns 0, or 1 when not collected. */
+int vb_debug_pose_mode_phases(long long* out16);
 
 /* Test hook: rotation vector -> matrix through the device and the host instantiation of the same deterministic
  * double-precision routine (csrc/host_math.h); the window pipeline relies on both giving identical bits. */

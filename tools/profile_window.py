@@ -29,8 +29,11 @@ from voldor_b200.pyvoldor_vo import load_library  # noqa: E402
 cnt = (C.c_longlong * 5)()
 load_library().vb_profile_counters(cnt)
 print("meanshift runs/iters/trials, robust runs/iters (all windows):", list(cnt))
-ph = (C.c_longlong * 8)()
+ph = (C.c_longlong * 16)()
 if load_library().vb_debug_pose_mode_phases(ph) == 0:
     tot = sum(ph[:6]) or 1
     print("robust-fit phase cycles (LU, E-step, level1, exchange, level2, M-step):", list(ph[:6]),
           [round(v / tot, 3) for v in ph[:6]])
+    tot = sum(ph[8:16]) or 1
+    print("mean-shift phase cycles (pool build, staging, weights, level1, exchange, level2, update, tail):",
+          list(ph[8:16]), [round(v / tot, 3) for v in ph[8:16]])

@@ -63,6 +63,7 @@ struct MeanshiftArgs {
     float good_init_confidence;
     PoolSource src;
     PoseTail tail;
+    long long* phase_cycles;  // optional [16]: clock64 totals of rank 0 at [8..15] (profiling)
 };
 
 // camera pose from the mean-shift mode (reference voldor/geometry.cpp:247-262 for a successive pose without robust
@@ -237,6 +238,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     const int Q = A.trial_only ? 1 : dims + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+    long long tick = clock64(), ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define VB_PHASE(k)                       \
+    do {                                  \
+        const long long now_ = clock64(); \
+        ph[k] += now_ - tick;             \
+        tick = now_;                      \
+    } while (0)
     int N;
     const float* space_g = A.src.space;
     if (A.src.rvecs) {
@@ -259,6 +267,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     S.nlb = (S.NB - rank + kCluster - 1) / kCluster;
     if (S.nlb < 0) S.nlb = 0;
     float* wv = smem;  // weights of the local slice
+    VB_PHASE(0);
     stage_slice(S, smem + (size_t)S.nlb * 512, A.slice_in_smem != 0);
     const int n_local = S.nlb * 512;
     float* prod = smem + (size_t)n_local * (1 + dims);  // FAST6: rows w, w*x_0 .. w*x_5
@@ -306,6 +315,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     }
     if (threadIdx.x == 0) done = 0, s_used_iters = 0, s_confidence = 0.f, s_wsum = 0.f;
     __syncthreads();
+    VB_PHASE(1);
 
     const int n_iters = A.trial_only ? 1 : A.max_iters;
 
@@ -335,6 +345,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
                 }
             }
             __syncthreads();
+            VB_PHASE(2);
             tree_level1(S, Q, X, cluster, [&](int q, int li) { return prod[(size_t)q * n_local + li]; });
         } else {
             for (int li = threadIdx.x; li < n_local; li += kThreads) {
@@ -353,9 +364,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
             tree_level1(S, Q, X, cluster,
                         [&](int q, int li) { return q == 0 ? wv[li] : f_mul(wv[li], S.x(li, q - 1)); });
         }
+        VB_PHASE(3);
         exchange_sync(X, cluster);
+        VB_PHASE(4);
         tree_level2(S.NB, Q, X, sums);
         __syncthreads();
+        VB_PHASE(5);
         if (warp == 0) {
             // host part of the reference iteration (meanshift.cu:112-133), one lane per dimension
             const float wsum = sums[0];
@@ -381,6 +395,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
             }
         }
         __syncthreads();
+        VB_PHASE(6);
         if (done) break;
     }
     if (rank == 0 && threadIdx.x == 0) {
@@ -392,7 +407,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
         out->aux_count = A.src.aux_count ? *A.src.aux_count : 0;
         out->n = N;
         if (A.tail.d_cams) pose_tail(A.tail, io_mean, dims, out->aux_count, N, out);
+        VB_PHASE(7);
+        if (A.phase_cycles)
+            for (int k = 0; k < 8; k++) A.phase_cycles[8 + k] += ph[k];
     }
+#undef VB_PHASE
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -710,8 +729,8 @@ int PoseMode::init() {
     VB_CUDA(cudaMalloc((void**)&d_rg_sums, 256 + kCluster * sizeof(int)));
     VB_CUDA(cudaMallocHost((void**)&h_rg_sums, 256));
     if (getenv("VB_POSE_MODE_PHASES")) {
-        VB_CUDA(cudaMalloc((void**)&d_phase_cycles, 8 * sizeof(long long)));
-        VB_CUDA(cudaMemset(d_phase_cycles, 0, 8 * sizeof(long long)));
+        VB_CUDA(cudaMalloc((void**)&d_phase_cycles, 16 * sizeof(long long)));
+        VB_CUDA(cudaMemset(d_phase_cycles, 0, 16 * sizeof(long long)));
     }
     VB_CUDA(cudaFuncSetAttribute(k_meanshift<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     VB_CUDA(cudaFuncSetAttribute(k_meanshift<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
@@ -727,6 +746,7 @@ static int run_meanshift(PoseMode& M, MeanshiftArgs& A, int n_plan, float* h_io_
     bool fast6;
     smem_plan(n_plan, A.dims, A.slice_in_smem, smem_bytes, nullptr, A.trial_only ? 1 : A.dims + 1, fast6);
     A.src.cta_counts = (int*)((char*)M.d_rg_sums + 256);
+    A.phase_cycles = M.d_phase_cycles;
     if (fast6)
         k_meanshift<true><<<kCluster, kThreads, smem_bytes, M.stream>>>(A, M.d_partials, M.d_result);
     else
@@ -842,6 +862,7 @@ int PoseMode::enqueue_from_hypotheses(int slot, const float* d_rvecs, const floa
     A.src.aux_count = d_aux_count;
     A.src.cta_counts = (int*)((char*)d_rg_sums + 256);
     A.tail = tail;
+    A.phase_cycles = d_phase_cycles;
     size_t smem_bytes;
     bool fast6;
     smem_plan(n_poses, dims, A.slice_in_smem, smem_bytes, nullptr, dims + 1, fast6);
