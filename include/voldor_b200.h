@@ -100,7 +100,7 @@ void vb_profile_counters(long long* out5);
  * variable VB_POSE_MODE_PHASES is set before the first call.  out16[0..5]: robust fit (LU, E-step, level-1 sums,
  * exchange barrier, level-2 sums, M-step); out16[8..15]: mean-shift (pool build, staging, weights, level-1 sums,
  * exchange barrier, level-2 sums, mean update, result + pose tail).  Returns 0, or 1 when not collected. */
-int vb_debug_pose_mode_phases(long long* out16);
+int vb_debug_pose_mode_phases(long long* out24);
 
 /* Test hook: rotation vector -> matrix through the device and the host instantiation of the same deterministic
  * double-precision routine (csrc/host_math.h); the window pipeline relies on both giving identical bits. */

@@ -29,7 +29,7 @@ from voldor_b200.pyvoldor_vo import load_library  # noqa: E402
 cnt = (C.c_longlong * 5)()
 load_library().vb_profile_counters(cnt)
 print("meanshift runs/iters/trials, robust runs/iters (all windows):", list(cnt))
-ph = (C.c_longlong * 16)()
+ph = (C.c_longlong * 24)()
 if load_library().vb_debug_pose_mode_phases(ph) == 0:
     tot = sum(ph[:6]) or 1
     print("robust-fit phase cycles (LU, E-step, level1, exchange, level2, M-step):", list(ph[:6]),

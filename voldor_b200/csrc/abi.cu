@@ -262,10 +262,10 @@ DLL_EXPORT void vb_profile_get(double* search_ms, long long* search_launches) {
     if (search_ms) *search_ms = p.search_ms;
     if (search_launches) *search_launches = p.search_launches;
 }
-DLL_EXPORT int vb_debug_pose_mode_phases(long long* out16) {
+DLL_EXPORT int vb_debug_pose_mode_phases(long long* out24) {
     vb::PoseMode& M = vb::global_pose_mode();
     if (!M.d_phase_cycles) return 1;
-    return (int)cudaMemcpy(out16, M.d_phase_cycles, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+    return (int)cudaMemcpy(out24, M.d_phase_cycles, 24 * sizeof(long long), cudaMemcpyDeviceToHost);
 }
 // rvec -> R through the device code path and through the host code path of the same source (csrc/host_math.h)
 namespace {

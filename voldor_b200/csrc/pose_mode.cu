@@ -142,6 +142,83 @@ __device__ int build_pool(const PoolSource& S, cg::cluster_group& cluster, int r
     return s_total;
 }
 
+// Same compaction without any exchange: every CTA scans the validity of ALL hypotheses itself (the table is small
+// and L2 resident: 8192 x 24 B), so each one knows every output position, and then loads only the hypotheses whose
+// tree block it owns — straight into its own shared-memory slice and into its part of the global pool (kept for later
+// consumers such as the robust fit).  Measured against exchanging positions/elements through distributed shared
+// memory (scalar remote stores: 16k cycles per launch) this takes ~3k.  At most 32 hypotheses per thread.
+// `smem` is this CTA's dynamic shared memory (layout: weights [n_local], slice [n_local][6], ...).
+__device__ int build_pool_local(const PoolSource& S, int rank, float* smem) {
+    // warp w scans the contiguous chunk [w*C, w*C + C) of hypotheses, lane l those at chunk + 32 j + l: coalesced,
+    // independent loads (memory-level parallelism), validity bit j kept in a per-lane mask
+    __shared__ int s_scan[kWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int J = (S.n_poses + kThreads - 1) / kThreads;  // rounds per lane, <= 32
+    const int chunk = warp * J * 32;
+    unsigned mask = 0;
+#pragma unroll 8
+    for (int j = 0; j < J; j++) {
+        const int i = chunk + j * 32 + lane;
+        if (i < S.n_poses) {
+            const float* r = S.rvecs + (size_t)i * 3;
+            const float* t = S.tvecs + (size_t)i * 3;
+            const float r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+            const float t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2);
+            if (isfinite(f_add(f_add(f_add(f_add(f_add(r0, r1), r2), t0), t1), t2))) mask |= 1u << j;
+        }
+    }
+    int warp_total = __popc(mask);
+    for (int o = 16; o >= 1; o >>= 1) warp_total += __shfl_xor_sync(0xffffffffu, warp_total, o);
+    if (lane == 0) s_scan[warp] = warp_total;
+    __syncthreads();
+    int base = 0, total = 0;
+    for (int k = 0; k < kWarps; k++) {
+        const int c = s_scan[k];
+        if (k < warp) base += c;
+        total += c;
+    }
+    const int NB = (total + 511) / 512;
+    const int my_nlb = max(0, (NB - rank + kCluster - 1) / kCluster);
+    float* slice = smem + (size_t)my_nlb * 512;
+    int running = base;
+    // second pass in groups of 4 rounds: the (L2-resident) reloads of a whole group are issued before any of its
+    // stores, otherwise every round would pay a full load latency
+    for (int j0 = 0; j0 < J; j0 += 4) {
+        float x[4][6];
+        bool valid[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int j = j0 + u;
+            valid[u] = j < J && ((mask >> j) & 1u);
+            if (valid[u]) {
+                const int i = chunk + j * 32 + lane;
+                const float* r = S.rvecs + (size_t)i * 3;
+                const float* t = S.tvecs + (size_t)i * 3;
+                x[u][0] = __ldg(r), x[u][1] = __ldg(r + 1), x[u][2] = __ldg(r + 2);
+                x[u][3] = __ldg(t), x[u][4] = __ldg(t + 1), x[u][5] = __ldg(t + 2);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned bal = __ballot_sync(0xffffffffu, valid[u]);
+            const int pos = running + __popc(bal & ((1u << lane) - 1u));
+            running += __popc(bal);
+            if (valid[u] && ((pos >> 9) % kCluster) == rank) {
+                float* g = S.pool_out + (size_t)pos * 6;
+                float* dst = slice + ((size_t)((pos >> 9) / kCluster) * 512 + (pos & 511)) * 6;
+#pragma unroll
+                for (int d = 0; d < 6; d++) {
+                    const float v = d < 3 ? f_mul(x[u][d], S.rvec_scale) : x[u][d];
+                    g[d] = v, dst[d] = v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (rank == 0 && threadIdx.x == 0) *S.used_out = total;
+    return total;
+}
+
 // element bookkeeping of one CTA: it owns tree blocks b = rank, rank+8, ... ; local block lb = b / 8
 struct Slice {
     int N, NB, nlb, rank, dims;
@@ -247,8 +324,16 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     } while (0)
     int N;
     const float* space_g = A.src.space;
+    bool staged = false;
     if (A.src.rvecs) {
-        N = build_pool(A.src, cluster, rank);
+        // dims == 6 here by construction (rvec, tvec)
+        staged = A.slice_in_smem && A.src.n_poses <= 32 * kThreads;
+        if (staged) {
+            N = build_pool_local(A.src, rank, smem);
+            cluster.sync();  // every CTA of the cluster is resident before anyone stores into its shared memory
+        } else {
+            N = build_pool(A.src, cluster, rank);
+        }
         space_g = A.src.pool_out;
     } else {
         N = A.src.d_n ? *A.src.d_n : A.src.n_host;
@@ -268,7 +353,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     if (S.nlb < 0) S.nlb = 0;
     float* wv = smem;  // weights of the local slice
     VB_PHASE(0);
-    stage_slice(S, smem + (size_t)S.nlb * 512, A.slice_in_smem != 0);
+    if (staged)
+        S.local = smem + (size_t)S.nlb * 512;
+    else
+        stage_slice(S, smem + (size_t)S.nlb * 512, A.slice_in_smem != 0);
     const int n_local = S.nlb * 512;
     float* prod = smem + (size_t)n_local * (1 + dims);  // FAST6: rows w, w*x_0 .. w*x_5
     const float two_var = f_add(A.kernel_var, A.kernel_var);  // 2*kernel_var
@@ -326,6 +414,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
             float cm[6];
 #pragma unroll
             for (int d = 0; d < 6; d++) cm[d] = c_mean[d];
+#pragma unroll 2
             for (int li = threadIdx.x; li < n_local; li += kThreads) {
                 float wgt = 0.f, x[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (S.gidx(li) < N) {
@@ -729,8 +818,8 @@ int PoseMode::init() {
     VB_CUDA(cudaMalloc((void**)&d_rg_sums, 256 + kCluster * sizeof(int)));
     VB_CUDA(cudaMallocHost((void**)&h_rg_sums, 256));
     if (getenv("VB_POSE_MODE_PHASES")) {
-        VB_CUDA(cudaMalloc((void**)&d_phase_cycles, 16 * sizeof(long long)));
-        VB_CUDA(cudaMemset(d_phase_cycles, 0, 16 * sizeof(long long)));
+        VB_CUDA(cudaMalloc((void**)&d_phase_cycles, 24 * sizeof(long long)));
+        VB_CUDA(cudaMemset(d_phase_cycles, 0, 24 * sizeof(long long)));
     }
     VB_CUDA(cudaFuncSetAttribute(k_meanshift<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     VB_CUDA(cudaFuncSetAttribute(k_meanshift<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
