@@ -12,7 +12,7 @@ namespace vb {
 namespace {
 
 constexpr int kBlock = 256;
-constexpr int kCompactTile = 512;  // pixels per tile of the single-pass compaction (shorter look-back chain)
+constexpr int kCompactTile = 1024;  // pixels per tile of the single-pass compaction (shorter look-back chain)
 
 struct CollectView {
     int N, w, h;
