@@ -530,6 +530,101 @@ __device__ __forceinline__ double d_add(double a, double b) { return __dadd_rn(a
 __device__ __forceinline__ double d_sub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double d_div(double a, double b) { return __ddiv_rn(a, b); }
 
+// 6x6 covariance step of one robust-fit iteration on ONE warp, the augmented matrix [a | b] held in registers: lane
+// c < 6 owns column c of a, lane 6 + c column c of b; pivot rows, multipliers and the upper triangle travel by
+// shuffles.  Operation for operation the sequential host code it mirrors (aux shim / cv::Matx66d: LU with partial
+// pivoting, det, back-substitution), every FP64 op individually rounded.  s_cov (packed lower triangle, float) is
+// replaced by its regularised version, s_cinv receives the inverse; returns false when det <= 0.
+__device__ __forceinline__ bool covariance_step_6x6(int lane, float* s_cov, float* s_cinv, bool shrink, double lambda) {
+    const unsigned full = 0xffffffffu;
+    const bool is_a = lane < 6, is_b = lane >= 6 && lane < 12;
+    const int c = is_a ? lane : lane - 6;
+    double col[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        col[r] = 0.0;
+        if (is_a) {
+            const int hi = r > c ? r : c, lo = r > c ? c : r;
+            col[r] = (double)s_cov[(hi * hi + hi) / 2 + lo];
+        } else if (is_b) {
+            col[r] = (r == c) ? 1.0 : 0.0;
+        }
+    }
+    if (shrink) {  // towards tr/n * I (Ledoit-Wolf with a fixed lambda)
+        double tr = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) tr = d_add(tr, __shfl_sync(full, col[i], i));
+        const double m = d_div(tr, 6.0);
+        const double lm = d_mul(lambda, m), oml = d_sub(1.0, lambda);
+        if (is_a) {
+#pragma unroll
+            for (int r = 0; r < 6; r++) col[r] = d_add(d_mul(lm, r == c ? 1.0 : 0.0), d_mul(oml, col[r]));
+        }
+    }
+    __syncwarp();  // every lane has read s_cov before anybody overwrites it
+    if (is_a) {  // the regularised covariance is the one reported on convergence (fit_robust_gaussian.cu:203)
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+            if (r >= c) s_cov[(r * r + r) / 2 + c] = (float)col[r];
+    }
+    double det = 1.0;
+    bool singular = false;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        if (singular) continue;
+        // partial pivoting on column i (owned by lane i): first maximum, strict '>'
+        int k = i;
+        double best = fabs(col[i]);
+#pragma unroll
+        for (int j = i + 1; j < 6; j++) {
+            const double v = fabs(col[j]);
+            if (v > best) best = v, k = j;
+        }
+        k = __shfl_sync(full, k, i);
+        best = __shfl_sync(full, best, i);
+        if (best < 2.220446049250313e-16 * 100) {
+            singular = true;
+            continue;
+        }
+        if (k != i) {
+            if ((is_a && c >= i) || is_b) {
+#pragma unroll
+                for (int j = i + 1; j < 6; j++)
+                    if (k == j) {
+                        const double tmp = col[i];
+                        col[i] = col[j];
+                        col[j] = tmp;
+                    }
+            }
+            det = -det;
+        }
+        const double piv = __shfl_sync(full, col[i], i);
+        const double d = d_div(-1.0, piv);
+#pragma unroll
+        for (int r = i + 1; r < 6; r++) {
+            const double alpha = d_mul(__shfl_sync(full, col[r], i), d);
+            if ((is_a && c > i) || is_b) col[r] = d_add(col[r], d_mul(alpha, col[i]));
+        }
+        det = d_mul(det, piv);
+    }
+    if (singular) det = 0.0;
+    if (!(det > 0)) return false;  // inverse only written for det > 0 (aux_funs.cpp:104-111)
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+        const double uii = __shfl_sync(full, col[i], i);
+        double acc = col[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; k++) acc = d_sub(acc, d_mul(__shfl_sync(full, col[i], k), col[k]));
+        if (is_b) col[i] = d_div(acc, uii);
+    }
+    if (is_b) {
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+            if (r >= c) s_cinv[(r * r + r) / 2 + c] = (float)col[r];
+    }
+    return true;
+}
+
 template <bool FAST6>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     k_robust_fit(const RobustArgs A, float* partials_g, RobustResult* out) {
@@ -582,7 +677,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     } while (0)
     for (iter = 0; iter < A.max_iters; iter++) {
         const Exchange X = exchange_for(iter, S.NB, s_part, 28, partials_g);
-        if (warp == 0) {
+        if (FAST6 && warp == 0) {
+            const bool ok = covariance_step_6x6(lane, s_cov, s_cinv, iter > 0 && A.covar_reg_lambda > 0,
+                                                (double)A.covar_reg_lambda);
+            if (lane == 0) s_lu_state = ok ? 0 : 2;
+        } else if (warp == 0) {
             // half -> full (double); shrink towards tr/n * I from the 2nd iteration on
             for (int e = lane; e < 36; e += 32) {
                 const int r = e / 6, c = e % 6;
