@@ -316,11 +316,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     long long tick = clock64(), ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define VB_PHASE(k)                       \
-    do {                                  \
-        const long long now_ = clock64(); \
-        ph[k] += now_ - tick;             \
-        tick = now_;                      \
+    const bool profiling = A.phase_cycles != nullptr && rank == 0 && threadIdx.x == 0;
+#define VB_PHASE(k)                           \
+    do {                                      \
+        if (profiling) {                      \
+            const long long now_ = clock64(); \
+            ph[k] += now_ - tick;             \
+            tick = now_;                      \
+        }                                     \
     } while (0)
     int N;
     const float* space_g = A.src.space;
@@ -669,11 +672,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
     int state = 0;       // 0 continue, 1 converged, 2 unreliable (uniform)
     int iter = 0;
     long long tick = clock64(), ph[6] = {0, 0, 0, 0, 0, 0};
-#define VB_PHASE(k)                                   \
-    do {                                              \
-        const long long now_ = clock64();             \
-        ph[k] += now_ - tick;                         \
-        tick = now_;                                  \
+    const bool profiling = A.phase_cycles != nullptr && rank == 0 && t == 0;
+#define VB_PHASE(k)                           \
+    do {                                      \
+        if (profiling) {                      \
+            const long long now_ = clock64(); \
+            ph[k] += now_ - tick;             \
+            tick = now_;                      \
+        }                                     \
     } while (0)
     for (iter = 0; iter < A.max_iters; iter++) {
         const Exchange X = exchange_for(iter, S.NB, s_part, 28, partials_g);
