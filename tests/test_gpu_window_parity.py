@@ -222,6 +222,9 @@ def test_vo_sequence_chained_windows_bit_exact():
     "--abs_resize_factor 0.5 --lambda 0.2 --meanshift_kernel_var 0.2",
     "--pose_sample_min_depth 6 --pose_sample_max_depth 9",
     "--meanshift_max_iters 3 --rg_max_iters 4",
+    # beyond the exchange-free pool build (16384 hypotheses): cluster-wide compaction.  Added after the round's GPU
+    # budget was spent, so not yet confirmed on hardware: reported, but not allowed to turn the suite red.
+    pytest.param("--n_poses_to_sample 20000", marks=pytest.mark.xfail(strict=False, reason="unverified on GPU")),
 ])
 def test_mono_window_flag_variants_bit_exact(flags):
     """configuration flags that switch code paths (solver, smoothing, truncation, start-sample fallbacks, ...)"""
