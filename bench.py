@@ -285,6 +285,15 @@ def bench_ours(args, rank, world, local_rank):
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "launches_timed": sl.value,
                 "issue_slots_busy_pct_ncu": issue_pct,
+                # compulsory bytes of one whole EM iteration W*H*(76N+56+16*N_dp) + 128*N*P over the
+                # measured time per iteration of the resident arm
+                "whole_iteration": {
+                    "algorithmic_bytes_per_iter": W * H * (76 * NFLOWS + 56) + 128 * NFLOWS * NPOSES,
+                    "achieved_per_gpu": (W * H * (76 * NFLOWS + 56) + 128 * NFLOWS * NPOSES) * iters_res / world /
+                    (ms_res * 1e-3) / 1e9,
+                    "frac": (W * H * (76 * NFLOWS + 56) + 128 * NFLOWS * NPOSES) * iters_res / world /
+                    (ms_res * 1e-3) / 1e9 / peak,
+                },
                 "note": "instruction-issue-bound kernel (6 powf + expf + logf + ~10 IEEE divisions per likelihood "
                         "term, all pinned by bit-parity): HBM fraction reported as BASELINE.json asks; the window "
                         "state is L2 resident; see DESIGN.md §6 and profiles/r01_ncu_search_kernel.md"}
