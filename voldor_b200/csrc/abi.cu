@@ -287,7 +287,7 @@ DLL_EXPORT int vb_debug_rvec_to_matrix(const float* rvecs, int n, float* R_devic
 }
 DLL_EXPORT int vb_debug_rand_speculate(int draw, int keep) {
     vb::LibcRandSnapshot snap;
-    if (!snap.take()) return 1;
+    if (!vb::LibcRandSnapshot::supported() || !snap.take()) return 1;
     for (int i = 0; i < draw; i++) (void)rand();
     snap.rewind();
     for (int i = 0; i < keep; i++) (void)rand();

@@ -15,6 +15,22 @@ namespace vb {
 
 class LibcRandSnapshot {
 public:
+    // One-time check that rewinding really replays rand(): true on glibc, where rand() is random() on the state array
+    // that initstate/setstate expose.  A libc whose rand() keeps private state (e.g. musl) fails the check and the
+    // caller falls back to drawing one number at a time.  Leaves the stream exactly where it was.
+    static bool supported() {
+        static const bool ok = [] {
+            LibcRandSnapshot probe;
+            if (!probe.take()) return false;
+            const int first = rand();
+            probe.rewind();
+            const int again = rand();
+            probe.rewind();
+            return first == again;
+        }();
+        return ok;
+    }
+
     // Capture the generator state.  Returns false when the state array has an unexpected shape, in which case the
     // caller must fall back to drawing one number at a time.
     bool take() {

@@ -988,7 +988,7 @@ int PoseMode::meanshift(const float* d_space, const float* h_space_for_init, con
         A.src.d_n = nullptr, A.src.n_host = N;
         d_n = nullptr;
         LibcRandSnapshot snap;
-        if (max_init_trials > 0 && max_init_trials <= kMaxTrialBatch && snap.take()) {
+        if (max_init_trials > 0 && max_init_trials <= kMaxTrialBatch && LibcRandSnapshot::supported() && snap.take()) {
             // all trials + the selection loop + the iteration in one launch; the libc stream is rewound to the
             // number of draws the reference's early-exit loop would have consumed (libc_rand.h)
             A.n_trials = max_init_trials;
