@@ -143,6 +143,12 @@ def test_rotation_helpers_roundtrip():
     back = np.ones(3, np.float32)
     L.oracle_matrix_to_rvec(R.ctypes.data_as(ffi.FP), back.ctypes.data_as(ffi.FP))
     assert np.array_equal(back, np.zeros(3, np.float32))
+    # every quadrant of the library's own sin/cos (csrc/host_math.h det::sincos), angles up to ~25 rad
+    for k in range(400):
+        rv = (rng.normal(0, 1, 3) * (0.02 + 0.06 * k)).astype(np.float32)
+        R = np.zeros(9, np.float32)
+        L.oracle_rvec_to_matrix(rv.ctypes.data_as(ffi.FP), R.ctypes.data_as(ffi.FP))
+        assert np.allclose(R.reshape(3, 3), synth.rodrigues(rv), atol=3e-7), (k, rv)
 
 
 def test_flag_grammar():
