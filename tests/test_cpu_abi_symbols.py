@@ -87,3 +87,38 @@ def test_libc_rand_speculation_is_invisible():
     a = libc.rand()
     assert lib.vb_debug_rand_speculate(7, 0) == 0
     libc.srand(1)
+
+
+def test_caller_compiled_against_the_reference_headers_links_against_this_library(tmp_path):
+    """library-level drop-in: a translation unit that includes the REFERENCE's own
+    gpu-kernels/gpu_kernels.h and voldor/py_export.h (where the checkout lies) and uses every entry point — with
+    the header's default arguments where it has them — links against libvoldor_b200.so with nothing else."""
+    ref = os.environ.get("VOLDOR_REFERENCE", "/root/reference")
+    hdr = os.path.join(ref, "gpu-kernels", "gpu_kernels.h")
+    if not os.path.exists(hdr):
+        pytest.skip("reference checkout not present")
+    src = tmp_path / "caller.cpp"
+    src.write_text(
+        '#include "%s"\n#include "%s"\n' % (hdr, os.path.join(ref, "voldor", "py_export.h")) +
+        "int main(int argc, char**) {\n"
+        "  if (argc < 1000) return 0;  // only has to link\n"
+        "  float f = 0; int i = 0; float* t[1] = {&f};\n"
+        "  i += meanshift_gpu(&f, 1.f, &f, &f, &i, false, 1, 1);              // default epsilon .. good_init\n"
+        "  i += fit_robust_gaussian(&f, &f, &f, 3.f, 0.f, &f, &i, 1, 1, 1e-5f, 1);\n"
+        "  i += collect_p3p_instances(t, t, &f, &f, t, t, &f, &f, 1, 1, 1, 0, .5f, 1.f, .1f, 1.f, 3);\n"
+        "  i += solve_batch_p3p_ap3p_gpu(&f, &f, &f, &f, &f, 1, 1);\n"
+        "  i += solve_batch_p3p_lambdatwist_gpu(&f, &f, &f, &f, &f, 1, 1);\n"
+        "  i += optimize_depth_gpu(t, t, t, t, t, t, t, &f, &f, &f, t, t, t, t, 1.f, 1, 0, 1, 1, 0.f, 1, 1, 1,\n"
+        "                          .1f, .1f, 1.f, 1.f, true, .5f, .9f, 1.f, false);\n"
+        "  i += align_frame_init_gpu(t, t, t, &f, 1.f, 1.f, 1, 1, 1);\n"
+        "  i += align_frame_eval_gpu(0, 0, &f, &f, &f, &f);                     // default apply_weights\n"
+        "  i += py_voldor_wrapper(&f, 0, 0, 0, 0, 0, 1, 1, 0, 0, 0, 1, 0, 1, 1, \"\", i, &f, &f, &f, &f);\n"
+        "  return i;\n}\n")
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(ffi.OURS)
+    r = subprocess.run(["g++", "-std=c++17", str(src), "-o", str(exe), "-L" + libdir, "-lvoldor_b200",
+                        "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # and it starts (loads the library, resolves every symbol eagerly) without a GPU
+    r = subprocess.run([str(exe)], capture_output=True, text=True, env=dict(os.environ, LD_BIND_NOW="1"))
+    assert r.returncode == 0, r.stderr
