@@ -84,3 +84,36 @@ def test_tracking_loss_restarts_without_priors():
     assert len(Tcw) == F + 1 and vo.lost == [1]
     assert state["priors"] == [False, True, False, True]
     assert np.allclose(Tcw[1], Tcw[2])  # the pose is kept across the lost frame
+
+
+def test_huber_slope_ignores_outliers():
+    rng = np.random.default_rng(3)
+    x = rng.uniform(1, 10, 2000)
+    y = 2.5 * x + rng.normal(0, 0.05, x.size)
+    y[:300] += rng.uniform(20, 60, 300)  # 15 % gross outliers
+    assert abs(vo_frontend.huber_slope(x, y) - 2.5) < 0.05
+    assert abs(np.dot(x, y) / np.dot(x, x) - 2.5) > 0.3  # plain least squares is pulled away
+
+
+def test_mono_scaled_mode_puts_depth_and_translation_on_the_metric_scale():
+    F, w, h = 3, 64, 48
+    win = synth.make_window(w, h, F, seed=6)
+    gt = _gt_poses6(win)
+    basefocal = 0.54 * float(win["fx"])
+    true_scale = 3.0  # the monocular solver returns depth / 3, translations / 3
+    disparity = (basefocal / win["depth_gt"]).astype(np.float32)
+
+    def stub(flows, *a, **kw):
+        n = flows.shape[0]
+        p = gt[:n].astype(np.float32).copy()
+        p[:, 3:] /= true_scale
+        return {"n_registered": n, "poses": p, "poses_covar": np.ones((n, 6, 6), np.float32),
+                "depth": (win["depth_gt"] / true_scale).astype(np.float32), "depth_conf": np.ones((h, w), np.float32)}
+
+    vo = vo_frontend.VisualOdometry(win["fx"], win["fy"], win["cx"], win["cy"], basefocal=basefocal, mode="mono-scaled",
+                                    winsize=F, solver=stub)
+    r = vo.step(win["flows"], disparity=disparity)
+    assert abs(r["scale"] - true_scale) < 1e-3
+    assert np.allclose(r["depth"], win["depth_gt"], rtol=1e-3)
+    assert np.allclose(r["poses"][:, 3:], gt[:F, 3:], rtol=1e-3, atol=1e-5)
+    assert np.allclose(r["poses_covar"][0, 0, 0], 1) and np.allclose(r["poses_covar"][0, 4, 4], true_scale ** 2, rtol=1e-3)

@@ -71,11 +71,30 @@ def eval_covisibility(depth, Tc1c2, K, mask=None, stride=4):
     return vis.sum() / ((w // stride) * (h // stride))
 
 
+def huber_slope(x, y, epsilon=1.35, iters=30):
+    """slope of y ~ k x without intercept under the Huber loss (iteratively reweighted least squares with a MAD scale);
+    stands in for sklearn's HuberRegressor(fit_intercept=False) used by voldor_slam.py:485-487"""
+    x, y = np.asarray(x, np.float64).ravel(), np.asarray(y, np.float64).ravel()
+    k = float(np.dot(x, y) / max(np.dot(x, x), 1e-300))
+    for _ in range(iters):
+        r = y - k * x
+        sigma = max(1.4826 * np.median(np.abs(r - np.median(r))), 1e-12)
+        w = np.minimum(1.0, epsilon * sigma / np.maximum(np.abs(r), 1e-300))
+        k_new = float(np.dot(w * x, y) / max(np.dot(w * x, x), 1e-300))
+        if abs(k_new - k) <= 1e-12 * max(1.0, abs(k)):
+            k = k_new
+            break
+        k = k_new
+    return k
+
+
 class VisualOdometry:
     """Frame-to-frame trajectory from dense flows.  `flows[i]` maps frame i to frame i+1.
 
-    mode 'mono':   config as voldor_slam.py:149 (`--meanshift_kernel_var 0.2 --delta 1.5 --max_iters 5`)
-    mode 'stereo': needs `basefocal` and one disparity map per window start (voldor_slam.py:145)
+    mode 'mono':        config as voldor_slam.py:153 (`--meanshift_kernel_var 0.2 --delta 1.5 --max_iters 5`)
+    mode 'mono-scaled': monocular solve, then depth and translations are put on the metric scale of a disparity map
+                        of the window start by a robust regression (voldor_slam.py:148-149,472-489)
+    mode 'stereo':      needs `basefocal` and one disparity map per window start (voldor_slam.py:145)
     """
 
     def __init__(self, fx, fy, cx, cy, basefocal=0.0, mode="mono", winsize=5, user_config="", use_depth_priors=True,
@@ -88,6 +107,9 @@ class VisualOdometry:
         else:
             self.config = "--silent --meanshift_kernel_var 0.2 --delta 1.5 --max_iters 5 "
         self.config += user_config
+        self.depth_scaling_max_pixels = 10000  # voldor_slam.py:93-94
+        self.depth_scaling_conf_thresh = 0.3
+        self._scaling_rng = np.random.default_rng(0)
         self.vostep_visibility_thresh = 0.8   # voldor_slam.py:88-90
         self.spakf_visibility_thresh = 0.8
         self.depth_covis_conf_thresh = 0.1
@@ -130,6 +152,23 @@ class VisualOdometry:
             self.fid_cur += 1
             r["vo_step"] = 1
             return r
+        if self.mode == "mono-scaled":
+            # metric scale from the disparity of the window start (voldor_slam.py:472-489)
+            mask = r["depth_conf"] > self.depth_scaling_conf_thresh
+            src = self.basefocal / r["depth"][mask]
+            dst = np.asarray(disparity, np.float32)[mask]
+            if src.size > self.depth_scaling_max_pixels:
+                idx = self._scaling_rng.permutation(src.size)[: self.depth_scaling_max_pixels]
+                src, dst = src[idx], dst[idx]
+            if src.size:
+                scale = float(np.clip(1.0 / huber_slope(src, dst), 0.1, 10.0))
+                r["depth"] = r["depth"] * scale
+                r["poses"] = r["poses"].copy()
+                r["poses"][:, 3:6] *= scale
+                r["poses_covar"] = r["poses_covar"].copy()
+                r["poses_covar"][:, :, 3:6] *= scale
+                r["poses_covar"][:, 3:6, :] *= scale
+                r["scale"] = scale
         T = [T6_to_T44(p) for p in r["poses"]]
         # how many frames to advance: while the window's depth map stays covisible (voldor_slam.py:496-504)
         vo_step, T_tmp = 0, np.eye(4)
