@@ -117,3 +117,46 @@ def test_mono_scaled_mode_puts_depth_and_translation_on_the_metric_scale():
     assert np.allclose(r["depth"], win["depth_gt"], rtol=1e-3)
     assert np.allclose(r["poses"][:, 3:], gt[:F, 3:], rtol=1e-3, atol=1e-5)
     assert np.allclose(r["poses_covar"][0, 0, 0], 1) and np.allclose(r["poses_covar"][0, 4, 4], true_scale ** 2, rtol=1e-3)
+
+
+def test_resize_flow_scales_vectors_and_matches_bilinear_centres():
+    H, W = 6, 8
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    flow = np.stack([2 * xx + 1, 3 * yy - 2], -1)  # linear fields are reproduced exactly away from the border
+    out = vo_frontend.resize_flow(flow, 4, 3)
+    assert out.shape == (3, 4, 2)
+    xs = (np.arange(4) + 0.5) * 2 - 0.5
+    ys = (np.arange(3) + 0.5) * 2 - 0.5
+    assert np.allclose(out[..., 0], (2 * xs[None, :] + 1) * 0.5 + 0 * ys[:, None])
+    assert np.allclose(out[..., 1], (3 * ys[:, None] - 2) * 0.5 + 0 * xs[None, :])
+    assert vo_frontend.resize_flow(flow, W, H) is flow
+
+
+def test_command_line_runs_a_sequence_from_flo_files(tmp_path, monkeypatch):
+    F, w, h = 5, 64, 48
+    win = synth.make_window(w, h, F, seed=8)
+    gt = _gt_poses6(win)
+    d = tmp_path / "flows"
+    d.mkdir()
+    for i in range(F):
+        formats.save_flow(str(d / f"{i:06d}.flo"), win["flows"][i])
+    seen = {}
+
+    def stub(flows, fx, fy, cx, cy, basefocal=0, config="", **kw):
+        start = seen.setdefault("next", 0)
+        n = flows.shape[0]
+        seen["shape"], seen["fx"], seen["config"], seen["basefocal"] = flows.shape, fx, config, basefocal
+        seen["next"] = start + n
+        return {"n_registered": n, "poses": gt[start:start + n].astype(np.float32),
+                "poses_covar": np.zeros((n, 6, 6), np.float32), "depth": np.full(flows.shape[1:3], 8.0, np.float32),
+                "depth_conf": np.ones(flows.shape[1:3], np.float32)}
+
+    monkeypatch.setattr(vo_frontend, "voldor", stub)
+    monkeypatch.setattr(vo_frontend.VisualOdometry.__init__, "__defaults__",
+                        vo_frontend.VisualOdometry.__init__.__defaults__[:5] + (stub, 1.0))
+    out = tmp_path / "poses.txt"
+    vo_frontend.main(["--mode", "mono", "--flow_dir", str(d), "--fx", "100", "--fy", "100", "--cx", "64", "--cy", "48",
+                      "--resize", "0.5", "--save_poses", str(out)])
+    assert seen["shape"][1:] == (24, 32, 2) and seen["fx"] == 50.0 and seen["basefocal"] == 25.0
+    assert "--abs_resize_factor 0.5" in seen["config"] and "--pose_sample_max_depth 25.0" in seen["config"]
+    assert formats.load_poses_kitti(str(out)).shape == (F + 1, 4, 4)

@@ -98,7 +98,11 @@ class VisualOdometry:
     """
 
     def __init__(self, fx, fy, cx, cy, basefocal=0.0, mode="mono", winsize=5, user_config="", use_depth_priors=True,
-                 solver=voldor):
+                 solver=voldor, rescale=1.0):
+        # voldor_slam.py:193-205 (set_cam_params): intrinsics follow the flow resize; without a baseline a virtual
+        # basefocal of half the focal length fixes the depth range in which pose samples are drawn
+        fx, fy, cx, cy = fx * rescale, fy * rescale, cx * rescale, cy * rescale
+        basefocal = basefocal * rescale if basefocal and basefocal > 0 else (fx + fy) * 0.25
         self.fx, self.fy, self.cx, self.cy, self.basefocal = fx, fy, cx, cy, basefocal
         self.K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float64)
         self.mode, self.winsize, self.use_depth_priors, self.solver = mode, winsize, use_depth_priors, solver
@@ -106,6 +110,7 @@ class VisualOdometry:
             self.config = "--silent --meanshift_kernel_var 0.1 --disp_delta 1 --delta 0.2 --max_iters 4 "
         else:
             self.config = "--silent --meanshift_kernel_var 0.2 --delta 1.5 --max_iters 5 "
+        self.config += f"--pose_sample_min_depth {basefocal / 200.0} --pose_sample_max_depth {basefocal / 1.0} "
         self.config += user_config
         self.depth_scaling_max_pixels = 10000  # voldor_slam.py:93-94
         self.depth_scaling_conf_thresh = 0.3
@@ -211,3 +216,71 @@ class VisualOdometry:
 
     def save_poses(self, path, format="KITTI"):
         formats.save_poses(path, self.Tcw, format)
+
+
+def resize_flow(flow, w, h):
+    """bilinear resize of a flow map with the vectors rescaled (voldor_slam.py:252-256; half-pixel centres like
+    cv2.resize's INTER_LINEAR)"""
+    H, W = flow.shape[:2]
+    if (W, H) == (w, h):
+        return flow
+    xs = (np.arange(w) + 0.5) * (W / w) - 0.5
+    ys = (np.arange(h) + 0.5) * (H / h) - 0.5
+    x0 = np.clip(np.floor(xs).astype(int), 0, W - 1)
+    y0 = np.clip(np.floor(ys).astype(int), 0, H - 1)
+    x1, y1 = np.minimum(x0 + 1, W - 1), np.minimum(y0 + 1, H - 1)
+    ax = np.clip(xs - x0, 0, 1)[None, :, None].astype(np.float32)
+    ay = np.clip(ys - y0, 0, 1)[:, None, None].astype(np.float32)
+    f = flow.astype(np.float32)
+    top = f[y0][:, x0] * (1 - ax) + f[y0][:, x1] * ax
+    bot = f[y1][:, x0] * (1 - ax) + f[y1][:, x1] * ax
+    out = top * (1 - ay) + bot * ay
+    out[..., 0] *= w / W
+    out[..., 1] *= h / H
+    return np.ascontiguousarray(out, np.float32)
+
+
+def main(argv=None):
+    """command line of the reference demo (demo/demo.py:4-18), restricted to what this front-end does"""
+    import argparse
+    import os
+
+    ap = argparse.ArgumentParser(description="dense-flow visual odometry with voldor_b200")
+    ap.add_argument("--mode", required=True, choices=["mono", "mono-scaled", "stereo"])
+    ap.add_argument("--flow_dir", required=True)
+    ap.add_argument("--disp_dir")
+    ap.add_argument("--fx", type=float, required=True)
+    ap.add_argument("--fy", type=float, required=True)
+    ap.add_argument("--cx", type=float, required=True)
+    ap.add_argument("--cy", type=float, required=True)
+    ap.add_argument("--bf", type=float, default=0)
+    ap.add_argument("--resize", type=float, default=0.5)
+    ap.add_argument("--abs_resize", type=float)
+    ap.add_argument("--save_poses")
+    ap.add_argument("--pose_format", default="KITTI", choices=["KITTI", "TartanAir"])
+    opt = ap.parse_args(argv)
+    abs_resize = opt.resize if opt.abs_resize is None else opt.abs_resize
+    names = sorted(os.listdir(opt.flow_dir))
+    first = formats.load_flow(os.path.join(opt.flow_dir, names[0]))
+    h, w = int(first.shape[0] * opt.resize), int(first.shape[1] * opt.resize)
+    flows = [resize_flow(formats.load_flow(os.path.join(opt.flow_dir, n)), w, h) for n in names]
+    disps = None
+    if opt.mode != "mono":
+        if not opt.disp_dir:
+            ap.error("--disp_dir is required for stereo and mono-scaled")
+        disps = []
+        for n in sorted(os.listdir(opt.disp_dir)):
+            d = formats.load_disparity(os.path.join(opt.disp_dir, n))
+            if d.shape != (h, w):  # voldor_slam.py:309-311
+                d = resize_flow(np.stack([d, d], -1), w, h)[..., 0]
+            disps.append(d)
+    vo = VisualOdometry(opt.fx, opt.fy, opt.cx, opt.cy, basefocal=opt.bf, mode=opt.mode, rescale=opt.resize,
+                        user_config=f"--abs_resize_factor {abs_resize} ")
+    vo.run(flows, disps)
+    print(f"{len(vo.Tcw)} poses, {len(vo.lost)} frames lost")
+    if opt.save_poses:
+        vo.save_poses(opt.save_poses, opt.pose_format)
+
+
+if __name__ == "__main__":
+    main()
