@@ -160,3 +160,29 @@ def test_command_line_runs_a_sequence_from_flo_files(tmp_path, monkeypatch):
     assert seen["shape"][1:] == (24, 32, 2) and seen["fx"] == 50.0 and seen["basefocal"] == 25.0
     assert "--abs_resize_factor 0.5" in seen["config"] and "--pose_sample_max_depth 25.0" in seen["config"]
     assert formats.load_poses_kitti(str(out)).shape == (F + 1, 4, 4)
+
+
+def test_sequence_with_the_cpu_port_as_solver_follows_the_ground_truth():
+    """whole chain (windows, keyframe priors built from own outputs, covisibility steps) with a real solver: the CPU
+    port of the hot path under the restated reference orchestration (test infrastructure)"""
+    import ffi
+    import oracle_host
+
+    w, h, F = 160, 120, 10
+    win = synth.make_window(w, h, F, seed=51)
+    boot = (win["Rs"][0], win["ts"][0], synth.noisy_depth(win, 0.05))
+
+    def solver(flows, fx, fy, cx, cy, **kw):
+        first = kw.get("depth_priors") is None
+        return oracle_host.run_window("cpu", flows, fx, fy, cx, cy, boot=boot if first else None, **kw)
+
+    ffi.libc_srand(31)
+    vo = vo_frontend.VisualOdometry(win["fx"], win["fy"], win["cx"], win["cy"], winsize=4, solver=solver,
+                                    user_config="--no_trunc_iters 1000 --n_poses_to_sample 2048 ")
+    T = vo.run(list(win["flows"]))
+    assert len(T) == F + 1 and vo.lost == []
+    T_gt = formats.accumulate_poses(_gt_poses6(win))
+    scale = np.linalg.norm(T[-1][:3, 3]) / np.linalg.norm(T_gt[-1][:3, 3])
+    for a, b in zip(T, T_gt):
+        assert np.abs(a[:3, :3] - b[:3, :3]).max() < 3e-2
+        assert np.linalg.norm(a[:3, 3] - b[:3, 3] * scale) < 0.1 * np.linalg.norm(T[-1][:3, 3])
