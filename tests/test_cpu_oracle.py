@@ -196,3 +196,78 @@ def test_cpu_port_against_reference_golden_collect_and_pose():
     pool = g["pool"]
     rc, m, conf, used = CPU.meanshift(pool, 0.1, g["ms_init"], True)
     assert used == int(g["ms_iters"]) and np.abs(m - g["ms_mean"]).max() < 1e-5 and abs(conf - float(g["ms_conf"])) < 1e-5
+
+
+def _cpu_align():
+    return ffi.GpuKernels(oracle_host.CPU, "cpu_")
+
+
+def test_cpu_align_frame_identity_and_analytic_translation():
+    """frame-alignment port (oracle/cpu_kernels.cpp, reference gpu-kernels/align_frame.cu): closed-form cases"""
+    L = _cpu_align()
+    w, h, N = 48, 36, 2
+    K = np.array([[40, 0, 24], [0, 40, 18], [0, 0, 1]], np.float32)
+    D, vbf = 5.0, 30.0
+    depths = np.full((N, h, w), D, np.float32)
+    weights = np.full((N, h, w), 0.7, np.float32)
+    images = np.zeros((N, h, w), np.float32)
+    assert L.align_init(images, depths, weights, K, vbf, 0.0) == 0
+    z9 = np.zeros(9, np.float32)
+    # identical frames, identity poses: every point lands on itself
+    rc, res, jac = L.align_eval(0, 1, z9, z9, w, h, True)
+    assert rc == 0 and np.isfinite(res).all() and np.abs(res).max() < 1e-6 and np.abs(jac).max() < 1e-4
+    # pure translation delta along the optical axis in front of a fronto-parallel plane at depth D:
+    # offset = delta along the normal, residual = sqrt(log(1 + wgt * (vbf / (D (D + delta)))^2 * delta^2 / 2))
+    delta = 0.4
+    p = z9.copy()
+    p[5] = delta
+    rc, res, jac = L.align_eval(0, 1, p, z9, w, h, True)
+    cy, cx = h // 2, w // 2
+    drw = (vbf / (D * (D + delta))) ** 2
+    raw = drw * 0.5 * delta ** 2
+    assert abs(res[cy, cx] - np.sqrt(np.log1p(0.7 * raw))) < 1e-5
+    # Jacobian w.r.t. tz before the loss is drw * delta; the loss multiplies by 0.5 / sqrt(loss) / (1 + r) * wgt
+    k = 0.5 / np.sqrt(np.log1p(0.7 * raw)) / (1 + 0.7 * raw) * 0.7
+    assert abs(jac[cy, cx, 5] - drw * delta * k) < 1e-4 * abs(drw * delta * k) + 1e-7
+    assert abs(jac[cy, cx, 3]) < 1e-6 and abs(jac[cy, cx, 4]) < 1e-6  # symmetric at the principal point
+    assert np.all(jac[..., 7:] == 0)  # no photometric term without images
+    # un-weighted evaluation differs only by the weight
+    rc, res_u, _ = L.align_eval(0, 1, p, z9, w, h, False)
+    assert abs(res_u[cy, cx] - np.sqrt(np.log1p(raw))) < 1e-5
+    # moving the point behind z = 1 or out of the image invalidates the pixel (NaN), Jacobian stays 0
+    p[5] = -4.5
+    rc, res, jac = L.align_eval(0, 1, p, z9, w, h, True)
+    assert np.isnan(res).all() and np.all(jac == 0)
+
+
+def test_cpu_align_frame_photometric_term():
+    L = _cpu_align()
+    w, h, N = 40, 30, 2
+    K = np.array([[35, 0, 20], [0, 35, 15], [0, 0, 1]], np.float32)
+    depths = np.full((N, h, w), 4.0, np.float32)
+    weights = np.ones((N, h, w), np.float32)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = (0.02 * xx + 0.01 * yy).astype(np.float32)
+    images = np.stack([img, img])
+    crw = 0.5
+    assert L.align_init(images, depths, weights, K, 25.0, crw) == 0
+    p_ref = np.zeros(9, np.float32)
+    p_tar = np.zeros(9, np.float32)
+    p_ref[8] = 0.3     # colour offset of the reference frame
+    p_tar[7] = 0.2     # colour scale of the target frame
+    rc, res, jac = L.align_eval(0, 1, p_ref, p_tar, w, h, False)
+    y, x = 12, 17      # interior pixel, identity geometry: only the colour residual is non-zero
+    c_ref = img[y, x] + 0.3
+    c_tar = img[y, x] * np.exp(0.0 - 0.2)
+    raw = crw * 0.5 * (c_ref - c_tar) ** 2
+    assert abs(res[y, x] - np.sqrt(np.log1p(raw))) < 1e-5
+    k = 0.5 / np.sqrt(np.log1p(raw)) / (1 + raw)
+    assert abs(jac[y, x, 8] - crw * (c_ref - c_tar) * k) < 1e-5
+    assert abs(jac[y, x, 7] - crw * (c_tar - c_ref) * c_tar * k) < 1e-5
+    # image gradient (0.3/0.1/0.1 stencil over 2 pixels -> 0.5 * 2 * slope) enters the translation Jacobian
+    gx, gy = 0.02, 0.01
+    dc = c_tar - c_ref
+    want_tx = crw * dc * (gx * K[0, 0] / 4.0) * k
+    want_ty = crw * dc * (gy * K[1, 1] / 4.0) * k
+    assert abs(jac[y, x, 3] - want_tx) < 2e-3 * abs(want_tx) + 1e-7
+    assert abs(jac[y, x, 4] - want_ty) < 2e-3 * abs(want_ty) + 1e-7

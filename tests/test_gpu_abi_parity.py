@@ -293,3 +293,32 @@ def test_rvec_to_matrix_identical_on_host_and_device():
     k = 5000
     want = synth.rodrigues(r[k].astype(np.float64))
     assert np.abs(R[k] - want).max() < 1e-6
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: not yet confirmed on hardware")
+@pytest.mark.parametrize("crw", [0.0, 0.5])
+def test_cpu_align_frame_port_against_the_reference_kernels(libs, crw):
+    """pins the CPU restatement of the frame alignment (oracle/cpu_kernels.cpp) to the reference's own kernels:
+    same NaN pattern away from the validity borders, 1e-3 relative on residual and Jacobian (libm vs libdevice,
+    emulated 8-bit texture weights)"""
+    import oracle_host
+
+    _, ref = libs
+    cpu = ffi.GpuKernels(oracle_host.CPU, "cpu_")
+    w, h, N = 96, 64, 3
+    win, images, depths, weights = _align_inputs(w, h, N, 13)
+    p_ref = np.array([0.01, -0.02, 0.005, 0.05, 0.02, 0.1, 0.01, 0.02, -0.01], np.float32)
+    p_tar = np.array([-0.005, 0.01, 0.0, 0.0, 0.01, -0.05, 0.0, -0.01, 0.02], np.float32)
+    outs = []
+    for lib in (cpu, ref):
+        assert lib.align_init(images, depths, weights, win["K"], 40.0, crw) == 0
+        rc, res, jac = lib.align_eval(0, 1, p_ref, p_tar, w, h, True)
+        assert rc == 0
+        outs.append((res, jac))
+    (res_c, jac_c), (res_r, jac_r) = outs
+    assert (np.isnan(res_c) != np.isnan(res_r)).mean() < 0.01
+    fin = np.isfinite(res_c) & np.isfinite(res_r)
+    assert fin.mean() > 0.5
+    assert (np.abs(res_c[fin] - res_r[fin]) <= 1e-3 * np.maximum(np.abs(res_r[fin]), 1e-3)).mean() > 0.99
+    scale = np.maximum(np.abs(jac_r[fin]), 1e-3 * np.abs(jac_r[fin]).max())
+    assert (np.abs(jac_c[fin] - jac_r[fin]) / scale <= 1e-3).mean() > 0.99
