@@ -85,6 +85,22 @@ int vb_py_voldor_wrapper_ex(const float* flows, const float* disparity, const fl
                             int N, int N_dp, int w, int h, const char* config, int* n_registered, float* poses,
                             float* poses_covar, float* depth, float* depth_conf, int* iters_run, float* stats);
 
+/* ---- execution contexts: several independent windows in flight on one GPU ----
+ *
+ * The reference keeps its device state in file statics (gpu-kernels/optimize_depth.cu:45-52,
+ * collect_p3p_instances.cu:29-34) and gets concurrency from a pool of worker PROCESSES
+ * (slam_py/voldor_slam.py:182-191).  Here one process holds up to vb_context_max() execution contexts, each owning
+ * what one reference process owns: streams, depth / rigidness / per-pixel RNG state, collector and pose-mode scratch,
+ * bootstrap override, profile counters and the start-sample rand() stream.  Every entry point of this library acts on
+ * the context selected by the CALLING HOST THREAD (default 0); calls on different contexts run concurrently, calls on
+ * one context serialise.  Context 0 draws start samples from the process-wide libc rand() exactly like the reference;
+ * contexts >= 1 own a private generator with glibc's rand() sequence (as a fresh process would), seeded 1. */
+int vb_context_select(int ctx);           /* bind this host thread to context ctx; returns the previous one, -1 if invalid */
+int vb_context_current(void);
+int vb_context_max(void);
+int vb_context_srand(unsigned int seed);  /* srand() of the current context's start-sample stream */
+int vb_context_rand(void);                /* one draw from it (test hook: consumption checks) */
+
 /* Select the CUDA device used by this process' state (default: current device). */
 int vb_set_device(int device);
 

@@ -62,6 +62,12 @@ class GpuKernels:
             f.argtypes = [C.c_int, C.c_int, FP, FP, FP, FP, C.c_int]
         except AttributeError:
             pass
+        try:
+            f = self._f("gblur_gpu")
+            f.restype = C.c_int
+            f.argtypes = [FP, FP, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int]
+        except AttributeError:
+            pass
 
     def _f(self, name):
         return getattr(self.lib, self.prefix + name)
@@ -157,6 +163,15 @@ class GpuKernels:
         rc = self._f("align_frame_eval_gpu")(ref_fid, tar_fid, _fp(pr), _fp(pt), _fp(res), _fp(jac),
                                              int(apply_weights))
         return rc, res, jac
+
+
+    def gblur(self, src, sigma, ksize=0):
+        """src: [depth, h, w] float32 -> (rc, blurred)"""
+        src = np.ascontiguousarray(src, np.float32)
+        d, h, w = src.shape
+        dst = np.full_like(src, -7.0)
+        rc = self._f("gblur_gpu")(_fp(src), _fp(dst), w, h, d, sigma, ksize)
+        return rc, dst
 
 
 def ours():

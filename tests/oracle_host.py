@@ -28,6 +28,18 @@ def lib():
 BACKENDS = {"ref": (ffi.REF, b"ref_"), "ours_abi": (ffi.OURS, b"vb_"), "cpu": (CPU, b"cpu_")}
 
 
+def fresh_reference_copy(tag):
+    """A private copy of the reference kernel library: dlopen of a distinct file gives distinct file statics (device
+    caches, per-pixel RNG planes), i.e. the state of a FRESH reference process inside this process.  Returns a backend
+    for run_window()."""
+    import shutil
+    import tempfile
+
+    dst = os.path.join(tempfile.gettempdir(), f"libgpu_kernels_ref_copy_{os.getpid()}_{tag}.so")
+    shutil.copyfile(ffi.REF, dst)
+    return (dst, b"ref_")
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(FP)
 
@@ -39,7 +51,8 @@ def _f(a):
 def run_window(backend, flows, fx, fy, cx, cy, basefocal=0, disparity=None, disparity_pconf=None, depth_priors=None,
                depth_prior_poses=None, depth_prior_pconfs=None, config="", boot=None):
     L = lib()
-    path, prefix = BACKENDS[backend]
+    # a backend is a name from BACKENDS or an explicit (library path, symbol prefix) pair
+    path, prefix = BACKENDS[backend] if isinstance(backend, str) else backend
     assert L.oracle_host_bind(path.encode(), prefix) == 0, f"cannot bind {backend}"
     flows = _f(flows)
     N, h, w = flows.shape[:3]

@@ -155,6 +155,40 @@ def test_baseline_config_shapes_bit_exact(name, w, h, N, iters, poses, kind):
     _compare(f"window {name} {w}x{h}x{N} resident-vs-ref", mine, ref)
 
 
+def test_c2_benchmarked_configuration_30_iterations_bit_exact():
+    """exactly what bench.py times (BASELINE.json configs[1]: 640x480, 8 flows, 30 EM iterations, 8192 hypotheses,
+    bench.py's seeds and flags): resident pipeline vs the reference kernels under the reference orchestration"""
+    import bench
+
+    win, boot = bench.make_inputs(0)
+    args = (win["flows"], win["fx"], win["fy"], win["cx"], win["cy"])
+    ffi.libc_srand(1000)
+    ref = oracle_host.run_window("ref", *args, config=bench.CONFIG, boot=boot)
+    voldor_b200.set_bootstrap_override(*boot)
+    ffi.libc_srand(1000)
+    mine = voldor_b200.voldor_ex(*args, config=bench.CONFIG)
+    voldor_b200.set_bootstrap_override()
+    assert ref["n_registered"] == bench.NFLOWS and ref["iters"] == bench.EM_ITERS
+    _compare("window C2 640x480x8 30 iterations (bench.py workload) resident-vs-ref", mine, ref)
+
+
+def test_c1_configuration_bit_exact():
+    """BASELINE.json configs[0]: single 320x240 frame, 4 flows, 10 EM iterations, monocular"""
+    w, h, N, iters = 320, 240, 4, 10
+    win = synth.make_window(w, h, N, seed=43)
+    boot = (win["Rs"][0], win["ts"][0], synth.noisy_depth(win, 0.05))
+    cfg = f"--silent --max_iters {iters} --no_trunc_iters 1000 --n_poses_to_sample 8192"
+    args = (win["flows"], win["fx"], win["fy"], win["cx"], win["cy"])
+    ffi.libc_srand(12)
+    ref = oracle_host.run_window("ref", *args, config=cfg, boot=boot)
+    voldor_b200.set_bootstrap_override(*boot)
+    ffi.libc_srand(12)
+    mine = voldor_b200.voldor_ex(*args, config=cfg)
+    voldor_b200.set_bootstrap_override()
+    assert ref["n_registered"] == N and ref["iters"] == iters
+    _compare("window C1 320x240x4 10 iterations resident-vs-ref", mine, ref)
+
+
 def test_vo_sequence_chained_windows_bit_exact():
     """A 10-flow sequence through the VO front-end (sliding windows, keyframe depth priors, covisibility steps):
     identical trajectories and identical per-window outputs from the product and from the reference kernels under
@@ -222,9 +256,10 @@ def test_vo_sequence_chained_windows_bit_exact():
     "--abs_resize_factor 0.5 --lambda 0.2 --meanshift_kernel_var 0.2",
     "--pose_sample_min_depth 6 --pose_sample_max_depth 9",
     "--meanshift_max_iters 3 --rg_max_iters 4",
-    # beyond the exchange-free pool build (16384 hypotheses): cluster-wide compaction.  Added after the round's GPU
-    # budget was spent, so not yet confirmed on hardware: reported, but not allowed to turn the suite red.
-    pytest.param("--n_poses_to_sample 20000", marks=pytest.mark.xfail(strict=False, reason="unverified on GPU")),
+    # beyond the exchange-free pool build (16384 hypotheses): cluster-wide compaction of the pose pool
+    "--n_poses_to_sample 20000",
+    # beyond 32768: the level-1 partial sums are exchanged through global memory instead of DSMEM
+    "--n_poses_to_sample 40000",
 ])
 def test_mono_window_flag_variants_bit_exact(flags):
     """configuration flags that switch code paths (solver, smoothing, truncation, start-sample fallbacks, ...)"""
@@ -268,7 +303,6 @@ def test_mono_window_with_nonfinite_flow_pixels_bit_exact():
     _compare("window mono with non-finite flow pixels", mine, ref)
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: not yet confirmed on hardware")
 def test_reference_cython_module_over_this_library_bit_exact():
     """The reference's own, unmodified pyvoldor_vo.pyx (built by integration/build_cython_binding.py against
     libvoldor_b200.so) called exactly like slam_py/voldor_slam.py:447-457 does, against the reference kernels under

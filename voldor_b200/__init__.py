@@ -3,6 +3,7 @@
 The compute lives in voldor_b200/libvoldor_b200.so (hand-written CUDA, built in-tree by `make lib` or
 `__graft_entry__.build()`).  There is no CPU fallback: importing the bindings without the library, or
 calling them without a CUDA device, raises."""
-from .pyvoldor_vo import voldor, load_library, set_bootstrap_override, voldor_ex  # noqa: F401
+from .pyvoldor_vo import (voldor, load_library, set_bootstrap_override, voldor_ex, select_context,  # noqa: F401
+                          context_srand)
 
-__all__ = ["voldor", "voldor_ex", "load_library", "set_bootstrap_override"]
+__all__ = ["voldor", "voldor_ex", "load_library", "set_bootstrap_override", "select_context", "context_srand"]

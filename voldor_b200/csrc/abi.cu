@@ -5,30 +5,15 @@
 // device-resident state objects, enqueue the kernels, download what the caller asked for.
 #include "../../include/gpu_kernels.h"
 #include "../../include/voldor_b200.h"
-#include "depth_em.cuh"
+#include "context.h"
 #include "host_math.h"
-#include "libc_rand.h"
-#include "pose_mode.cuh"
-#include "pose_sampler.cuh"
 #include <mutex>
 
-namespace {
-
-// grow-only device scratch
-struct DevBuf {
-    float* ptr = nullptr;
-    size_t cap = 0;
-    int ensure(size_t n) {
-        if (n <= cap) return 0;
-        if (ptr) cudaFree(ptr);
-        ptr = nullptr, cap = 0;
-        VB_CUDA(cudaMalloc((void**)&ptr, n * sizeof(float)));
-        cap = n;
-        return 0;
-    }
-};
-
-}  // namespace
+// Every entry point works on the calling host thread's execution context (context.h; context 0 unless the thread
+// selected another one) and holds that context's mutex for the duration of the call.
+#define VB_ENTER_CONTEXT()                \
+    vb::Context& cx = vb::current_context(); \
+    std::lock_guard<std::recursive_mutex> lock(cx.mutex)
 
 // ---------------------------------------------------------------------------------------------------
 int optimize_depth_gpu(float* h_flows[], float* h_rigidnesses[], float* h_o_rigidnesses[], float* h_depth_priors[],
@@ -38,9 +23,9 @@ int optimize_depth_gpu(float* h_flows[], float* h_rigidnesses[], float* h_o_rigi
                        int n_rand_samples, int global_prop_step, int local_prop_width, float lambda, float omega,
                        float disp_delta, float delta, bool fb_smooth, float s0_ems_prob, float no_change_prob,
                        float range_factor, bool update_rigidness_only) {
-    std::lock_guard<std::recursive_mutex> lock(vb::state_mutex());
+    VB_ENTER_CONTEXT();
     if (N > vb::kMaxFrames || N_dp > vb::kMaxPriorFrames) return (int)cudaErrorInvalidValue;
-    vb::DepthEM& E = vb::global_depth_em();
+    vb::DepthEM& E = cx.E;
     E.shared_flows = nullptr;
     E.overlap_smoothing = false;  // ABI calls hand the raw maps back to the host after every step
     if (int e = E.ensure(w, h, N, N_dp)) return e;
@@ -95,9 +80,9 @@ int collect_p3p_instances(float* h_flows[], float* h_rigidnesses[], float* h_dep
                           float* h_ts[], float* h_o_p2_map, float* h_o_p3_map, int N, int w, int h, int active_idx,
                           float rigidness_thresh, float rigidness_sum_thresh, float sample_min_depth,
                           float sample_max_depth, int max_trace_on_flow) {
-    std::lock_guard<std::recursive_mutex> lock(vb::state_mutex());
+    VB_ENTER_CONTEXT();
     if (N > vb::kMaxFrames) return (int)cudaErrorInvalidValue;
-    vb::Collector& C = vb::global_collector();
+    vb::Collector& C = cx.C;
     if (int e = C.ensure(w, h, N)) return e;
     cudaStream_t s = C.stream;
     C.flows_own.ensure(w, h, N, true);
@@ -135,11 +120,11 @@ int collect_p3p_instances(float* h_flows[], float* h_rigidnesses[], float* h_dep
 // ---------------------------------------------------------------------------------------------------
 static int solve_batch_host(float* h_p3s, float* h_p2s, float* h_o_rvecs, float* h_o_tvecs, float* h_K, int N_pts,
                             int N_poses, bool ap3p) {
-    std::lock_guard<std::recursive_mutex> lock(vb::state_mutex());
-    static DevBuf p2, p3, rv, tv;
-    static float K4[4] = {0, 0, 0, 0};  // fx, fy, cx, cy survive a NULL h_K like the reference's constants
-    static cudaStream_t s = nullptr;
-    if (!s) VB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    VB_ENTER_CONTEXT();
+    vb::DevBuf &p2 = cx.abi.p2, &p3 = cx.abi.p3, &rv = cx.abi.rv, &tv = cx.abi.tv;
+    float* K4 = cx.abi.K4;
+    if (!cx.abi.p3p_stream) VB_CUDA(cudaStreamCreateWithFlags(&cx.abi.p3p_stream, cudaStreamNonBlocking));
+    cudaStream_t s = cx.abi.p3p_stream;
     if (h_K) K4[0] = h_K[0], K4[1] = h_K[4], K4[2] = h_K[2], K4[3] = h_K[5];
     if (p2.ensure(((size_t)N_pts + 1) * 2) || p3.ensure(((size_t)N_pts + 1) * 3) || rv.ensure((size_t)N_poses * 3) ||
         tv.ensure((size_t)N_poses * 3))
@@ -172,9 +157,9 @@ int solve_batch_p3p_lambdatwist_gpu(float* h_p3s, float* h_p2s, float* h_o_rvecs
 int meanshift_gpu(float* h_space, float kernel_var, float* h_io_mean, float* h_o_confidence, int* used_iters,
                   bool use_external_init_mean, int N, int dims, float epsilon, int max_iters, int max_init_trials,
                   float good_init_confidence) {
-    std::lock_guard<std::recursive_mutex> lock(vb::state_mutex());
-    static DevBuf space;
-    vb::PoseMode& M = vb::global_pose_mode();
+    VB_ENTER_CONTEXT();
+    vb::DevBuf& space = cx.abi.ms_space;
+    vb::PoseMode& M = cx.M;
     if (int e = M.init()) return e;
     if (space.ensure((size_t)N * dims)) return (int)cudaErrorMemoryAllocation;
     VB_CUDA(cudaMemcpyAsync(space.ptr, h_space, (size_t)N * dims * sizeof(float), cudaMemcpyHostToDevice, M.stream));
@@ -185,9 +170,9 @@ int meanshift_gpu(float* h_space, float kernel_var, float* h_io_mean, float* h_o
 int fit_robust_gaussian(float* h_space, float* h_io_mean, float* h_io_covar, float trunc_sigma,
                         float covar_reg_lambda, float* h_o_density, int* used_iters, int N, int dims, float epsilon,
                         int max_iters) {
-    std::lock_guard<std::recursive_mutex> lock(vb::state_mutex());
-    static DevBuf space;
-    vb::PoseMode& M = vb::global_pose_mode();
+    VB_ENTER_CONTEXT();
+    vb::DevBuf& space = cx.abi.rg_space;
+    vb::PoseMode& M = cx.M;
     if (int e = M.init()) return e;
     if (space.ensure((size_t)N * dims)) return (int)cudaErrorMemoryAllocation;
     VB_CUDA(cudaMemcpyAsync(space.ptr, h_space, (size_t)N * dims * sizeof(float), cudaMemcpyHostToDevice, M.stream));
@@ -247,23 +232,23 @@ DLL_EXPORT int vb_optimize_depth_gpu(float** h_flows, float** h_rigidnesses, flo
 
 DLL_EXPORT int vb_set_device(int device) { return (int)cudaSetDevice(device); }
 DLL_EXPORT void vb_profile_enable(int on) {
-    vb::KernelProfile& p = vb::kernel_profile();
+    vb::KernelProfile& p = vb::current_context().prof;
     p.enabled = on != 0;
     p.search_ms = 0, p.search_launches = 0;
     p.meanshift_runs = p.meanshift_iters = p.meanshift_trials = p.robust_runs = p.robust_iters = 0;
 }
 DLL_EXPORT void vb_profile_counters(long long* out5) {
-    vb::KernelProfile& p = vb::kernel_profile();
+    vb::KernelProfile& p = vb::current_context().prof;
     out5[0] = p.meanshift_runs, out5[1] = p.meanshift_iters, out5[2] = p.meanshift_trials;
     out5[3] = p.robust_runs, out5[4] = p.robust_iters;
 }
 DLL_EXPORT void vb_profile_get(double* search_ms, long long* search_launches) {
-    vb::KernelProfile& p = vb::kernel_profile();
+    vb::KernelProfile& p = vb::current_context().prof;
     if (search_ms) *search_ms = p.search_ms;
     if (search_launches) *search_launches = p.search_launches;
 }
 DLL_EXPORT int vb_debug_pose_mode_phases(long long* out24) {
-    vb::PoseMode& M = vb::global_pose_mode();
+    vb::PoseMode& M = vb::current_context().M;
     if (!M.d_phase_cycles) return 1;
     return (int)cudaMemcpy(out24, M.d_phase_cycles, 24 * sizeof(long long), cudaMemcpyDeviceToHost);
 }
@@ -286,11 +271,13 @@ DLL_EXPORT int vb_debug_rvec_to_matrix(const float* rvecs, int n, float* R_devic
     return (int)e;
 }
 DLL_EXPORT int vb_debug_rand_speculate(int draw, int keep) {
-    vb::LibcRandSnapshot snap;
-    if (!vb::LibcRandSnapshot::supported() || !snap.take()) return 1;
-    for (int i = 0; i < draw; i++) (void)rand();
-    snap.rewind();
-    for (int i = 0; i < keep; i++) (void)rand();
+    vb::Context& cx = vb::current_context();
+    std::lock_guard<std::recursive_mutex> lock(cx.mutex);
+    vb::RandStream& r = *cx.rnd;
+    if (!r.snapshot()) return 1;
+    for (int i = 0; i < draw; i++) (void)r.next();
+    r.rewind();
+    for (int i = 0; i < keep; i++) (void)r.next();
     return 0;
 }
 DLL_EXPORT const char* vb_version(void) { return "voldor_b200 0.1 sm_100a"; }

@@ -300,26 +300,29 @@ __global__ void __launch_bounds__(128)
         for (int i = 0; i < kAlignParams; i++) jac[i] = J[i];
 }
 
-// separable Gaussian with border renormalisation (gblur.cu:12-44); vertical then horizontal like the reference
+// separable Gaussian with border renormalisation (gblur.cu:12-44); vertical then horizontal like the reference.
+// Rounding points as in the reference build: the tap products are fused into the running sum.
 template <int VERTICAL>
-__global__ void k_gblur(const float* src, float* dst, int w, int h, const float* gk, int hw) {
+__global__ void __launch_bounds__(256) k_gblur(const float* __restrict__ src, float* __restrict__ dst, int w, int h,
+                                               const float* __restrict__ gk, int hw) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int d = blockIdx.z;
     if (x >= w || y >= h) return;
     const float* s = src + (size_t)d * w * h;
-    float sum = gk[0] * s[(size_t)y * w + x];
+    float sum = __fmul_rn(gk[0], s[(size_t)y * w + x]);
     float sum_w = gk[0];
     for (int k = 1; k < hw; k++) {
+        const float g = gk[k];
         if (VERTICAL) {
-            if (y + k < h) sum += gk[k] * s[(size_t)(y + k) * w + x], sum_w += gk[k];
-            if (y - k >= 0) sum += gk[k] * s[(size_t)(y - k) * w + x], sum_w += gk[k];
+            if (y + k < h) sum = __fmaf_rn(g, s[(size_t)(y + k) * w + x], sum), sum_w = __fadd_rn(sum_w, g);
+            if (y - k >= 0) sum = __fmaf_rn(g, s[(size_t)(y - k) * w + x], sum), sum_w = __fadd_rn(sum_w, g);
         } else {
-            if (x + k < w) sum += gk[k] * s[(size_t)y * w + x + k], sum_w += gk[k];
-            if (x - k >= 0) sum += gk[k] * s[(size_t)y * w + x - k], sum_w += gk[k];
+            if (x + k < w) sum = __fmaf_rn(g, s[(size_t)y * w + x + k], sum), sum_w = __fadd_rn(sum_w, g);
+            if (x - k >= 0) sum = __fmaf_rn(g, s[(size_t)y * w + x - k], sum), sum_w = __fadd_rn(sum_w, g);
         }
     }
-    dst[(size_t)d * w * h + (size_t)y * w + x] = sum / sum_w;
+    dst[(size_t)d * w * h + (size_t)y * w + x] = __fdiv_rn(sum, sum_w);
 }
 
 AlignView make_view(AlignState& S) {
@@ -363,8 +366,10 @@ int align_frame_init_gpu(float* h_images[], float* h_depths[], float* h_weights[
         VB_CUDA(cudaMalloc((void**)&S.jacobian, npx * kAlignParams * sizeof(float)));
         S.cap = npx;
     }
-    S.K.fx = h_K[0], S.K.cx = h_K[2], S.K.fy = h_K[4], S.K.cy = h_K[5];
-    S.K.fxi = 1.f / h_K[0], S.K.cxi = -h_K[2] / h_K[0], S.K.fyi = 1.f / h_K[4], S.K.cyi = -h_K[5] / h_K[4];
+    if (h_K) {  // NULL keeps the cached intrinsics, like the other entry points of this library
+        S.K.fx = h_K[0], S.K.cx = h_K[2], S.K.fy = h_K[4], S.K.cy = h_K[5];
+        S.K.fxi = 1.f / h_K[0], S.K.cxi = -h_K[2] / h_K[0], S.K.fyi = 1.f / h_K[4], S.K.cyi = -h_K[5] / h_K[4];
+    }
     VB_RETURN_IF_CUDA_ERROR();
     const dim3 b(32, 4), g(VB_DIV_CEIL(w, 32), VB_DIV_CEIL(h, 4), N);
     k_align_prepare<<<g, b, 0, s>>>(make_view(S), S.normals.ptr, S.normals.pitch, S.ddepths.ptr, S.ddepths.pitch,
@@ -415,7 +420,11 @@ DLL_EXPORT int vb_align_frame_eval_gpu(int ref_fid, int tar_fid, const float* h_
 DLL_EXPORT int vb_gblur_gpu(const float* h_src, float* h_dst, int w, int h, int depth, float sigma, int ksize) {
     static std::mutex m;
     std::lock_guard<std::mutex> lock(m);
+    // grow-only scratch: two image stacks + the half kernel (the reference allocates and frees a GMat per call)
     static cudaStream_t s = nullptr;
+    static float *a = nullptr, *b = nullptr, *gk = nullptr;
+    static size_t cap = 0;
+    if (w <= 0 || h <= 0 || depth <= 0 || !h_src || !h_dst) return (int)cudaErrorInvalidValue;
     if (!s) VB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     if (ksize == 0) ksize = std::max((int)std::ceil(6 * sigma), 3);
     const int half = ksize / 2 + 1;
@@ -423,10 +432,17 @@ DLL_EXPORT int vb_gblur_gpu(const float* h_src, float* h_dst, int w, int h, int 
     float hk[128];
     for (int i = 0; i < half; i++) hk[i] = expf(-(float)(i * i) / (float)(2 * sigma * sigma));
     const size_t n = (size_t)w * h * depth;
-    float *a, *b, *gk;
-    VB_CUDA(cudaMalloc((void**)&a, n * sizeof(float)));
-    VB_CUDA(cudaMalloc((void**)&b, n * sizeof(float)));
-    VB_CUDA(cudaMalloc((void**)&gk, 128 * sizeof(float)));
+    if (!gk) VB_CUDA(cudaMalloc((void**)&gk, 128 * sizeof(float)));
+    if (n > cap) {
+        if (a) cudaFree(a), cudaFree(b);
+        a = b = nullptr, cap = 0;
+        VB_CUDA(cudaMalloc((void**)&a, n * sizeof(float)));
+        if (cudaMalloc((void**)&b, n * sizeof(float)) != cudaSuccess) {
+            cudaFree(a), a = nullptr;
+            return (int)cudaErrorMemoryAllocation;
+        }
+        cap = n;
+    }
     VB_CUDA(cudaMemcpyAsync(gk, hk, half * sizeof(float), cudaMemcpyHostToDevice, s));
     VB_CUDA(cudaMemcpyAsync(a, h_src, n * sizeof(float), cudaMemcpyDefault, s));
     const dim3 bl(32, 8), gr(VB_DIV_CEIL(w, 32), VB_DIV_CEIL(h, 8), depth);
@@ -434,7 +450,6 @@ DLL_EXPORT int vb_gblur_gpu(const float* h_src, float* h_dst, int w, int h, int 
     vb::k_gblur<0><<<gr, bl, 0, s>>>(b, a, w, h, gk, half);
     VB_CUDA(cudaMemcpyAsync(h_dst, a, n * sizeof(float), cudaMemcpyDefault, s));
     VB_CUDA(cudaStreamSynchronize(s));
-    cudaFree(a), cudaFree(b), cudaFree(gk);
     VB_RETURN_IF_CUDA_ERROR();
     return 0;
 }

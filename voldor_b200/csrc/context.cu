@@ -1,0 +1,49 @@
+// Registry of execution contexts (context.h) and their C entry points (include/voldor_b200.h).
+#include "context.h"
+#include "../../include/py_export.h"
+#include "../../include/voldor_b200.h"
+
+namespace vb {
+
+namespace {
+std::mutex g_registry_mutex;
+Context* g_contexts[kMaxContexts] = {nullptr};
+thread_local int t_selected = 0;
+}  // namespace
+
+Context* context_at(int id) {
+    if (id < 0 || id >= kMaxContexts) return nullptr;
+    std::lock_guard<std::mutex> lock(g_registry_mutex);
+    if (!g_contexts[id]) g_contexts[id] = new Context(id);  // lives for the rest of the process, like the reference's statics
+    return g_contexts[id];
+}
+
+Context& current_context() { return *context_at(t_selected); }
+
+int select_context(int id) {
+    if (!context_at(id)) return -1;
+    const int prev = t_selected;
+    t_selected = id;
+    return prev;
+}
+
+}  // namespace vb
+
+extern "C" {
+
+VB_EXPORT int vb_context_select(int ctx) { return vb::select_context(ctx); }
+VB_EXPORT int vb_context_current(void) { return vb::current_context().id; }
+VB_EXPORT int vb_context_max(void) { return vb::kMaxContexts; }
+VB_EXPORT int vb_context_srand(unsigned int seed) {
+    vb::Context& cx = vb::current_context();
+    std::lock_guard<std::recursive_mutex> lock(cx.mutex);
+    cx.rnd->seed(seed);
+    return 0;
+}
+VB_EXPORT int vb_context_rand(void) {
+    vb::Context& cx = vb::current_context();
+    std::lock_guard<std::recursive_mutex> lock(cx.mutex);
+    return cx.rnd->next();
+}
+
+}  // extern "C"

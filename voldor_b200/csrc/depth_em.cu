@@ -692,6 +692,8 @@ static int pick_search_block_y(int w, int h, int n_sm) {
     static const int forced = [] { const char* e = getenv("VB_SEARCH_BLOCK_Y"); return e ? atoi(e) : 0; }();
     if (forced > 0 && forced <= 8) return forced;
     static int per_sm[9] = {0};
+    static std::mutex per_sm_mutex;  // contexts call this from different host threads
+    std::lock_guard<std::mutex> lock(per_sm_mutex);
     const int cand[4] = {6, 5, 8, 4};
     int best = 8;
     double best_eff = -1;
@@ -789,7 +791,8 @@ int DepthEM::run(int N, int N_dp, const DepthHyper& hp, bool update_rigidness_on
             }
             VB_RETURN_IF_CUDA_ERROR();
         }
-        KernelProfile& prof = kernel_profile();
+        KernelProfile none;
+        KernelProfile& prof = this->prof ? *this->prof : none;
         if (prof.enabled) {
             if (!prof.ev0) cudaEventCreate(&prof.ev0), cudaEventCreate(&prof.ev1);
             cudaEventRecord(prof.ev0, s);
@@ -840,21 +843,6 @@ int DepthEM::run(int N, int N_dp, const DepthHyper& hp, bool update_rigidness_on
         VB_RETURN_IF_CUDA_ERROR();
     }
     return 0;
-}
-
-std::recursive_mutex& state_mutex() {
-    static std::recursive_mutex m;
-    return m;
-}
-
-DepthEM& global_depth_em() {
-    static DepthEM inst;
-    return inst;
-}
-
-KernelProfile& kernel_profile() {
-    static KernelProfile inst;
-    return inst;
 }
 
 }  // namespace vb

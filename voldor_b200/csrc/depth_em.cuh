@@ -2,8 +2,9 @@
 //
 // Replaces the reference's optimize_depth.cu file-static GMats + 26-launch host driver
 // (reference: gpu-kernels/optimize_depth.cu:24-52 state, :293-520 driver, fb_smooth.h:17-109).
-// One DepthEM instance per process/device keeps what the reference keeps in file statics, including the
-// per-pixel XORWOW streams that advance across calls and windows (optimize_depth.cu:357-361).
+// One DepthEM instance per execution context (context.h; context 0 = the reference's one-per-process state) keeps
+// what the reference keeps in file statics, including the per-pixel XORWOW streams that advance across calls and
+// windows (optimize_depth.cu:357-361).
 #pragma once
 #include <mutex>
 #include "common.cuh"
@@ -19,7 +20,10 @@ struct DepthHyper {
     float range_factor;
 };
 
+struct KernelProfile;
+
 struct DepthEM {
+    KernelProfile* prof = nullptr;  // the owning context's counters
     // geometry of the cached window
     int w = 0, h = 0;
     // device state
@@ -67,12 +71,6 @@ struct DepthEM {
     int run(int N, int N_dp, const DepthHyper& hp, bool update_rigidness_only);
 };
 
-DepthEM& global_depth_em();
-
-// Guards the process-wide device state (DepthEM, Collector, PoseMode, hypothesis tables): every ABI entry point and
-// the window pipeline take it, so calls from different host threads serialise (the reference relies on the GIL).
-std::recursive_mutex& state_mutex();
-
 // Optional in-library timing of the dominant kernel (fused cost + random search), CUDA events on the launching
 // stream.  Off by default; bench.py switches it on for the roofline figure (vb_profile_* in voldor_b200.h).
 struct KernelProfile {
@@ -85,6 +83,5 @@ struct KernelProfile {
     long long meanshift_runs = 0, meanshift_iters = 0, meanshift_trials = 0;
     long long robust_runs = 0, robust_iters = 0;
 };
-KernelProfile& kernel_profile();
 
 }  // namespace vb

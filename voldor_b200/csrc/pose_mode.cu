@@ -948,11 +948,12 @@ static int run_meanshift(PoseMode& M, MeanshiftArgs& A, int n_plan, float* h_io_
     VB_RETURN_IF_CUDA_ERROR();
     VB_CUDA(cudaMemcpyAsync(M.h_result, M.d_result, sizeof(MeanshiftResult), cudaMemcpyDeviceToHost, M.stream));
     VB_CUDA(cudaStreamSynchronize(M.stream));
-    KernelProfile& prof = kernel_profile();
-    if (A.trial_only)
-        prof.meanshift_trials++;
-    else
-        prof.meanshift_runs++, prof.meanshift_iters += M.h_result->used_iters;
+    if (M.prof) {
+        if (A.trial_only)
+            M.prof->meanshift_trials++;
+        else
+            M.prof->meanshift_runs++, M.prof->meanshift_iters += M.h_result->used_iters;
+    }
     if (!A.trial_only && M.h_result->used_iters > 0) {
         if (h_o_confidence) *h_o_confidence = M.h_result->confidence;
         if (used_iters) *used_iters = M.h_result->used_iters;
@@ -987,27 +988,27 @@ int PoseMode::meanshift(const float* d_space, const float* h_space_for_init, con
         if (N <= 0) return (int)cudaErrorInvalidValue;
         A.src.d_n = nullptr, A.src.n_host = N;
         d_n = nullptr;
-        LibcRandSnapshot snap;
-        if (max_init_trials > 0 && max_init_trials <= kMaxTrialBatch && LibcRandSnapshot::supported() && snap.take()) {
+        if (!rnd) return (int)cudaErrorInvalidValue;
+        if (max_init_trials > 0 && max_init_trials <= kMaxTrialBatch && rnd->snapshot()) {
             // all trials + the selection loop + the iteration in one launch; the libc stream is rewound to the
             // number of draws the reference's early-exit loop would have consumed (libc_rand.h)
             A.n_trials = max_init_trials;
             A.good_init_confidence = good_init_confidence;
-            for (int trial = 0; trial < max_init_trials; trial++) A.trial_idx[trial] = rand() % N;
+            for (int trial = 0; trial < max_init_trials; trial++) A.trial_idx[trial] = rnd->next() % N;
             if (used_iters) *used_iters = 0;
             if (int e = run_meanshift(*this, A, N, h_io_mean, h_o_confidence, used_iters)) return e;
             const int used = h_result->trials_used;
-            kernel_profile().meanshift_trials += used;
+            if (prof) prof->meanshift_trials += used;
             if (used < max_init_trials) {
-                snap.rewind();
-                for (int trial = 0; trial < used; trial++) (void)rand();
+                rnd->rewind();
+                for (int trial = 0; trial < used; trial++) (void)rnd->next();
             }
             return 0;
         }
         float best_conf = 0;
         int best_idx = -1;
         for (int trial = 0; trial < max_init_trials; trial++) {
-            const int idx_rand = (rand() % N);
+            const int idx_rand = (rnd->next() % N);
             MeanshiftArgs T = A;
             T.center_idx = idx_rand, T.trial_only = 1;
             if (int e = run_meanshift(*this, T, N, nullptr, nullptr, nullptr)) return e;
@@ -1072,8 +1073,8 @@ int PoseMode::fetch_results(int n_slots) {
     if (n_slots <= 0) return 0;
     VB_CUDA(cudaMemcpyAsync(h_result, d_result, (size_t)n_slots * sizeof(MeanshiftResult), cudaMemcpyDeviceToHost, stream));
     VB_CUDA(cudaStreamSynchronize(stream));
-    KernelProfile& prof = kernel_profile();
-    for (int i = 0; i < n_slots; i++) prof.meanshift_runs++, prof.meanshift_iters += h_result[i].used_iters;
+    if (prof)
+        for (int i = 0; i < n_slots; i++) prof->meanshift_runs++, prof->meanshift_iters += h_result[i].used_iters;
     return 0;
 }
 
@@ -1105,7 +1106,7 @@ int PoseMode::fit_robust_gaussian(const float* d_space, int N, int dims, float s
     VB_RETURN_IF_CUDA_ERROR();
     VB_CUDA(cudaMemcpyAsync(h_res, d_res, sizeof(RobustResult), cudaMemcpyDeviceToHost, stream));
     VB_CUDA(cudaStreamSynchronize(stream));
-    kernel_profile().robust_runs++, kernel_profile().robust_iters += h_res->used_iters;
+    if (prof) prof->robust_runs++, prof->robust_iters += h_res->used_iters;
 
     if (h_res->reliable) {
         if (h_o_density) *h_o_density = h_res->density;
@@ -1118,11 +1119,6 @@ int PoseMode::fit_robust_gaussian(const float* d_space, int N, int dims, float s
         for (int d = 0; d < dims; d++) h_io_mean[d] = h_res->mean[d];
     }
     return h_res->reliable ? 0 : 1;  // cudaSuccess / !cudaSuccess (fit_robust_gaussian.cu:281-284)
-}
-
-PoseMode& global_pose_mode() {
-    static PoseMode inst;
-    return inst;
 }
 
 }  // namespace vb

@@ -36,7 +36,12 @@ struct PoseTail {
     float inv_rvec_scale;
 };
 
+struct RandStream;
+struct KernelProfile;
+
 struct PoseMode {
+    RandStream* rnd = nullptr;      // start-sample stream of the owning context (libc_rand.h); never null when used
+    KernelProfile* prof = nullptr;  // the owning context's counters
     cudaStream_t stream = nullptr;
     MeanshiftResult* d_result = nullptr;  // device, kMaxFrames slots (slot 0 is the synchronous API's)
     MeanshiftResult* h_result = nullptr;  // pinned host mirror
@@ -72,7 +77,5 @@ struct PoseMode {
                             float* h_io_covar, float trunc_sigma, float covar_reg_lambda, float* h_o_density,
                             int* used_iters, float epsilon, int max_iters);
 };
-
-PoseMode& global_pose_mode();
 
 }  // namespace vb

@@ -6,6 +6,8 @@
 #include "p3p_ap3p.cuh"
 #include "rotation.cuh"
 #include <curand_kernel.h>
+#include <algorithm>
+#include <mutex>
 
 namespace vb {
 
@@ -353,21 +355,19 @@ int Collector::collect(int N, const CollectParams& P, bool compact) {
     return 0;
 }
 
-Collector& global_collector() {
-    static Collector inst;
-    return inst;
-}
-
-int HypothesisDraws::ensure(int n_poses, cudaStream_t s) {
-    if (n_poses <= capacity) return 0;
-    if (u4) cudaFree(u4);
-    u4 = nullptr, capacity = 0;
-    VB_CUDA(cudaMalloc((void**)&u4, (size_t)n_poses * sizeof(float4)));
-    k_hypothesis_draws<<<VB_DIV_CEIL(n_poses, 128), 128, 0, s>>>(u4, n_poses);
-    VB_RETURN_IF_CUDA_ERROR();
-    VB_CUDA(cudaStreamSynchronize(s));  // other streams may consume the table
-    capacity = n_poses;
-    return 0;
+const float4* HypothesisDraws::ensure(int n_poses, cudaStream_t s) {
+    static std::mutex m;
+    static float4* table = nullptr;  // superseded (smaller) tables stay allocated: kernels in flight may read them
+    static int capacity = 0;
+    std::lock_guard<std::mutex> lock(m);
+    if (n_poses <= capacity) return table;
+    const int cap = std::max(n_poses, 16384);
+    float4* fresh = nullptr;
+    if (cudaMalloc((void**)&fresh, (size_t)cap * sizeof(float4)) != cudaSuccess) return nullptr;
+    k_hypothesis_draws<<<VB_DIV_CEIL(cap, 128), 128, 0, s>>>(fresh, cap);
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) return nullptr;
+    table = fresh, capacity = cap;
+    return table;
 }
 
 HypothesisDraws& global_draws() {
@@ -378,14 +378,15 @@ HypothesisDraws& global_draws() {
 int solve_batch_p3p_device(const float* d_p3s, const float* d_p2s, const int* d_n_pts, int n_pts_host, float fx,
                            float fy, float cx, float cy, float* d_rvecs, float* d_tvecs, int n_poses,
                            bool use_ap3p, cudaStream_t s) {
-    if (int e = global_draws().ensure(n_poses, s)) return e;
+    const float4* u4 = global_draws().ensure(n_poses, s);
+    if (!u4) return (int)cudaErrorMemoryAllocation;
     const int nb = VB_DIV_CEIL(n_poses, 32);
     if (use_ap3p)
-        k_solve_p3p<true><<<nb, 32, 0, s>>>(d_p2s, d_p3s, d_n_pts, n_pts_host, global_draws().u4, fx, fy, cx, cy,
-                                            d_rvecs, d_tvecs, n_poses);
+        k_solve_p3p<true><<<nb, 32, 0, s>>>(d_p2s, d_p3s, d_n_pts, n_pts_host, u4, fx, fy, cx, cy, d_rvecs, d_tvecs,
+                                            n_poses);
     else
-        k_solve_p3p<false><<<nb, 32, 0, s>>>(d_p2s, d_p3s, d_n_pts, n_pts_host, global_draws().u4, fx, fy, cx, cy,
-                                             d_rvecs, d_tvecs, n_poses);
+        k_solve_p3p<false><<<nb, 32, 0, s>>>(d_p2s, d_p3s, d_n_pts, n_pts_host, u4, fx, fy, cx, cy, d_rvecs, d_tvecs,
+                                             n_poses);
     VB_RETURN_IF_CUDA_ERROR();
     return 0;
 }

@@ -50,15 +50,14 @@ struct Collector {
     int collect(int N, const CollectParams& P, bool compact);
 };
 
-Collector& global_collector();
-
 // Per-hypothesis uniform draws of the reference sampler: 4 values of curand_uniform() from
 // XORWOW(seed 233, subsequence idx, offset 0) — constants, because the reference re-seeds on every call
 // (solve_batch_lambdatwist.cu:44-48,81).  Tabulated once per capacity.
+// The table is a constant of (seed, index), so ONE table serves every execution context of the process: ensure() is
+// serialised, and a table that was handed out is never freed (another context's kernels may still be reading it).
 struct HypothesisDraws {
-    float4* u4 = nullptr;
-    int capacity = 0;
-    int ensure(int n_poses, cudaStream_t s);
+    // returns the table (>= n_poses entries) or nullptr on a CUDA error
+    const float4* ensure(int n_poses, cudaStream_t s);
 };
 HypothesisDraws& global_draws();
 

@@ -15,10 +15,8 @@
 #include "../../include/voldor_b200.h"
 #include "bootstrap.h"
 #include "config.h"
-#include "depth_em.cuh"
+#include "context.h"
 #include "host_math.h"
-#include "pose_mode.cuh"
-#include "pose_sampler.cuh"
 #include "residual_model.cuh"
 #include <chrono>
 #include <cstdlib>
@@ -40,13 +38,6 @@ struct Camera {  // reference: voldor/utils.h:30-76
     float pose_rigidness_density = 0;
     int last_used_ms_iters = 0, last_used_gu_iters = 0;
 };
-
-struct BootstrapOverride {
-    bool valid = false;
-    float R[9], t[3];
-    std::vector<float> depth;
-    int w = 0, h = 0;
-} g_bootstrap;
 
 // ---------------------------------------------------------------------------------------------------
 // small kernels
@@ -118,9 +109,11 @@ __global__ void k_depth_conf(float* out, int w, int h, const float* rig, int rpi
 }
 
 // ---------------------------------------------------------------------------------------------------
-// the window object (one per call, device state lives in the process-wide singletons)
+// the window object (one per call; the device state lives in the execution context it runs on, context.h)
 // ---------------------------------------------------------------------------------------------------
 struct Window {
+    Context& ctx;
+    explicit Window(Context& c) : ctx(c), E(c.E), C(c.C), M(c.M) {}
     Config cfg;
     int w = 0, h = 0, n_flows = 0, n_flows_init = 0, n_depth_priors = 0;
     int iters_cur = 0, iters_remain = 0;
@@ -130,32 +123,14 @@ struct Window {
     float depth_scale_pending = 1.f;  // host depth == device depth * this (normalize_world_scale)
     bool depth_on_device_valid = false;
 
-    DepthEM& E = global_depth_em();
-    Collector& C = global_collector();
-    PoseMode& M = global_pose_mode();
+    DepthEM& E;
+    Collector& C;
+    PoseMode& M;
     cudaStream_t s = nullptr;
 
-    // scratch (process-wide, grow only)
-    struct Scratch {
-        float *rvecs = nullptr, *tvecs = nullptr, *pool = nullptr;
-        int* d_used = nullptr;
-        int pose_cap = 0;
-        double *sum_partial = nullptr, *sums = nullptr;
-        double* h_sums = nullptr;
-        int* h_counts = nullptr;  // pinned: [0]=n_points, [1]=pool_used
-        float* stage = nullptr;   // pinned staging for outputs
-        size_t stage_cap = 0;
-        float* d_out = nullptr;
-        size_t out_cap = 0;
-        float* d_disp = nullptr;
-        size_t disp_cap = 0;
-        CamBlock* d_cams = nullptr;  // device-resident poses of the pipelined camera loop
-        CamBlock* h_cams = nullptr;  // pinned staging
-    };
-    static Scratch& scratch() {
-        static Scratch sc;
-        return sc;
-    }
+    // scratch (per context, grow only)
+    using Scratch = WindowScratch;
+    Scratch& scratch() { return ctx.ws; }
 
     double t_cameras = 0, t_depth = 0, t_io = 0;
 
@@ -544,6 +519,7 @@ struct Window {
     }
 
     int bootstrap(const float* flows_pt) {
+        const BootstrapOverride& g_bootstrap = ctx.boot;
         if (g_bootstrap.valid && g_bootstrap.w == w && g_bootstrap.h == h) {
             memcpy(cams[0].R, g_bootstrap.R, sizeof(g_bootstrap.R));
             memcpy(cams[0].t, g_bootstrap.t, sizeof(g_bootstrap.t));
@@ -641,9 +617,10 @@ int run_window(const float* flows_pt, const float* disparity_pt, const float* di
                float fx, float fy, float cx, float cy, float basefocal, int N, int N_dp, int w, int h,
                const char* config_pt, int* n_registered, float* poses_pt, float* poses_covar_pt, float* depth_pt,
                float* depth_conf_pt, int* iters_run, float* stats) {
-    std::lock_guard<std::recursive_mutex> lock(state_mutex());
+    Context& context = current_context();
+    std::lock_guard<std::recursive_mutex> lock(context.mutex);
     auto t0 = std::chrono::high_resolution_clock::now();
-    Window W;
+    Window W(context);
     W.cfg.fx = fx, W.cfg.cx = cx, W.cfg.fy = fy, W.cfg.cy = cy, W.cfg.basefocal = basefocal;
     W.cfg.read(config_pt);
     if (W.cfg.cpu_p3p) {
@@ -714,13 +691,15 @@ VB_EXPORT int vb_bootstrap_from_flow(const float* flow, int w, int h, const floa
 }
 
 VB_EXPORT int vb_set_bootstrap_override(int valid, const float* R9, const float* t3, const float* depth, int w, int h) {
-    std::lock_guard<std::recursive_mutex> lock(vb::state_mutex());
-    vb::g_bootstrap.valid = valid != 0;
+    vb::Context& cx = vb::current_context();  // the override belongs to the calling thread's execution context
+    std::lock_guard<std::recursive_mutex> lock(cx.mutex);
+    vb::BootstrapOverride& b = cx.boot;
+    b.valid = valid != 0;
     if (!valid) return 0;
-    memcpy(vb::g_bootstrap.R, R9, 9 * sizeof(float));
-    memcpy(vb::g_bootstrap.t, t3, 3 * sizeof(float));
-    vb::g_bootstrap.depth.assign(depth, depth + (size_t)w * h);
-    vb::g_bootstrap.w = w, vb::g_bootstrap.h = h;
+    memcpy(b.R, R9, 9 * sizeof(float));
+    memcpy(b.t, t3, 3 * sizeof(float));
+    b.depth.assign(depth, depth + (size_t)w * h);
+    b.w = w, b.h = h;
     return 0;
 }
 

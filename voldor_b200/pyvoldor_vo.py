@@ -32,8 +32,26 @@ def load_library():
     lib.vb_set_bootstrap_override.restype = C.c_int
     lib.vb_set_bootstrap_override.argtypes = [C.c_int, FP, FP, FP, C.c_int, C.c_int]
     lib.vb_version.restype = C.c_char_p
+    lib.vb_context_select.restype = C.c_int
+    lib.vb_context_select.argtypes = [C.c_int]
+    lib.vb_context_srand.argtypes = [C.c_uint]
     _lib = lib
     return lib
+
+
+def select_context(ctx):
+    """Bind the calling Python thread to execution context `ctx` (0 .. vb_context_max()-1); returns the previous one.
+    Contexts are independent copies of the library's device state: windows issued from different threads on
+    different contexts run concurrently on the GPU (ctypes releases the GIL for the duration of a call)."""
+    prev = load_library().vb_context_select(int(ctx))
+    if prev < 0:
+        raise ValueError(f"invalid execution context {ctx}")
+    return prev
+
+
+def context_srand(seed):
+    """srand() of the current context's start-sample stream (context 0: the process-wide libc rand())"""
+    return load_library().vb_context_srand(int(seed))
 
 
 def _ptr(a):
