@@ -1,0 +1,41 @@
+#!/bin/bash
+# One gpurun call's worth of measurements; everything lands in gpurun_out/<tag>/.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh r02a tests bench sanitize probe'
+tag=$1; shift
+out=gpurun_out/$tag
+mkdir -p $out
+for what in "$@"; do
+case $what in
+tests)
+  python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > $out/pytest.log
+  tail -3 $out/pytest.log ;;
+bench)
+  for m in 1 2 3 4; do
+    python bench.py --steps 6 --warmup 3 --inflight $m --no-extras --no-cpu-baseline --no-parity > $out/bench_inflight$m.json 2> $out/bench_inflight$m.err
+    python - <<PY
+import json
+try:
+    l=json.loads(open("$out/bench_inflight$m.json").read().strip().splitlines()[-1])
+    print("inflight $m value", round(l["value"],1), "e2e", round(l["e2e"]["value"],1), "lat", l["latency"])
+except Exception as e:
+    print("inflight $m failed", e, open("$out/bench_inflight$m.err").read()[-1500:])
+PY
+  done ;;
+benchfull)
+  python bench.py > $out/bench.json 2> $out/bench.err; tail -c 3000 $out/bench.json; tail -5 $out/bench.err
+  python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_ref.json 2> $out/bench_ref.err; tail -c 600 $out/bench_ref.json ;;
+sanitize)
+  for tool in memcheck racecheck synccheck; do
+    timeout 900 compute-sanitizer --tool $tool --kernel-name kns=vb --print-limit 20 python tools/sanitize_target.py > $out/sanitizer_$tool.log 2>&1
+    echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize_target" $out/sanitizer_$tool.log | tail -3
+  done ;;
+sanitizebig)
+  timeout 900 compute-sanitizer --tool memcheck --kernel-name kns=vb --print-limit 20 python tools/sanitize_target.py --big > $out/sanitizer_memcheck_big.log 2>&1
+  echo "memcheck big rc=$?"; grep -E "ERROR SUMMARY|sanitize_target" $out/sanitizer_memcheck_big.log | tail -3 ;;
+probe)
+  tools/_build/tex_probe 27 > $out/tex_probe.json 2>&1; cat $out/tex_probe.json ;;
+launches)
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $out/launches.csv python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline --no-parity > $out/bench_under_ncu.log 2>&1
+  echo "ncu launches rc=$?"; wc -l $out/launches.csv ;;
+esac
+done
