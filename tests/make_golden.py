@@ -42,3 +42,22 @@ rc, m, conf, used = ref.meanshift(pool, 0.1, init, True)
 np.savez_compressed(os.path.join(out, "pose_stage_64x48x3.npz"), seed=seed, rig_in=rig_in, depth_in=depth_in, p2=p2,
                     p3=p3, rvecs=rv, tvecs=tv, pool=pool, ms_init=init, ms_mean=m, ms_conf=conf, ms_iters=used)
 print("golden written to", out, "instances", int(ok.sum()), "pool", pool.shape, "ms iters", used)
+
+# 3. minimal solvers alone: 8192 hypotheses of both solvers on the instances of a 160x120x4 window (camera 2), pinned
+#    against by tests/test_cpu_p3p_quad.py (host build of the product's solver arithmetic)
+seed3, w3, h3, N3 = 23, 160, 120, 4
+win3 = synth.make_window(w3, h3, N3, seed=seed3)
+rig3 = np.random.default_rng(6).uniform(0.4, 1.0, (N3, h3, w3)).astype(np.float32)
+rc, q2, q3 = ref.collect(w3, h3, N3, 2, flows=list(win3["flows"]), rig=list(rig3), depth=synth.noisy_depth(win3, 0.02),
+                         K=win3["K"], Rs=list(win3["Rs"]), ts=list(win3["ts"]))
+assert rc == 0
+ok3 = np.isfinite(q2.sum(-1) + q3.sum(-1))
+pts2, pts3 = q2[ok3], q3[ok3]
+rc, rv_lt, tv_lt = ref.solve_p3p(pts3, pts2, win3["K"], 8192)
+assert rc == 0
+rc, rv_ap, tv_ap = ref.solve_p3p(pts3, pts2, win3["K"], 8192, ap3p=True)
+assert rc == 0
+np.savez_compressed(os.path.join(out, "p3p_hypotheses_160x120.npz"), seed=seed3, K=win3["K"], p2s=pts2, p3s=pts3,
+                    rvecs_lambdatwist=rv_lt, tvecs_lambdatwist=tv_lt, rvecs_ap3p=rv_ap, tvecs_ap3p=tv_ap)
+print("p3p golden:", pts2.shape[0], "instances; finite lambdatwist", int(np.isfinite(tv_lt.sum(1)).sum()), "ap3p",
+      int(np.isfinite(tv_ap.sum(1)).sum()))

@@ -4,9 +4,11 @@
 #include "geometry.cuh"
 #include "p3p_lambdatwist.cuh"
 #include "p3p_ap3p.cuh"
+#include "p3p_twist_quad.cuh"
 #include "rotation.cuh"
 #include <curand_kernel.h>
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 namespace vb {
@@ -251,6 +253,72 @@ __global__ void __launch_bounds__(32)
     rvecs[idx * 3 + 2] = rv[2];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Quad-lane sampler: four consecutive lanes share one hypothesis (p3p_twist_quad.cuh).  Lane q of a quad fetches the
+// q-th sampled correspondence (one gather per point instead of every thread gathering all four), the quad exchanges
+// them with shuffles, every lane solves ITS candidate (plane, root) of the minimal problem, and the winner of the
+// 4th-point test — found with four shuffles in the reference's scan order — converts its rotation and writes the
+// hypothesis.  Same draws, same candidates, same arithmetic per candidate as one thread per hypothesis
+// (reference: solve_batch_lambdatwist.cu:11-42), a quarter of the dependent chain.
+// ------------------------------------------------------------------------------------------------
+constexpr int kQuadBlock = 64;  // 16 hypotheses per block
+template <int SOLVER>
+__global__ void __launch_bounds__(kQuadBlock)
+    k_solve_p3p_quad(const float* __restrict__ p2s, const float* __restrict__ p3s, const int* d_n_pts, int n_pts_host,
+                     const float4* __restrict__ u4, float fx, float fy, float cx, float cy, float* rvecs, float* tvecs,
+                     int n_poses) {
+    const int gid = blockIdx.x * kQuadBlock + threadIdx.x;
+    const int hyp = gid >> 2, slot = gid & 3;
+    if (hyp >= n_poses) return;  // whole quads leave together (n_poses*4 threads are launched, rounded up to blocks)
+    const int lane = threadIdx.x & 31, qbase = lane & ~3;
+    const unsigned qmask = 0xFu << qbase;
+    const int n_pts = d_n_pts ? *d_n_pts : n_pts_host;
+    int best = -1;
+    quad::Pose P;
+    if (n_pts >= 4 || !d_n_pts) {
+        const float4 u = u4[hyp];
+        const float mine = slot == 0 ? u.x : slot == 1 ? u.y : slot == 2 ? u.z : u.w;
+        const int i = (int)f_mul(mine, (float)n_pts);  // can equal n_pts when u == 1; buffers are padded
+        const float pu = p2s[i * 2], pv = p2s[i * 2 + 1];
+        const float px = p3s[i * 3], py = p3s[i * 3 + 1], pz = p3s[i * 3 + 2];
+        float uv[8];
+        quad::Vec3f X[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uv[2 * k] = __shfl_sync(qmask, pu, qbase + k);
+            uv[2 * k + 1] = __shfl_sync(qmask, pv, qbase + k);
+            X[k].x = __shfl_sync(qmask, px, qbase + k);
+            X[k].y = __shfl_sync(qmask, py, qbase + k);
+            X[k].z = __shfl_sync(qmask, pz, qbase + k);
+        }
+        float err = 0.f;
+        const bool mine_exists = quad::twist_lane(slot, uv, X, fx, fy, cx, cy, P, err);
+        bool exists[4];
+        float errs[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            exists[k] = __shfl_sync(qmask, (int)mine_exists, qbase + k) != 0;
+            errs[k] = __shfl_sync(qmask, err, qbase + k);
+        }
+        best = quad::pick_by_fourth_point(exists, errs);
+    }
+    if (best < 0) {
+        if (slot == 0) {
+            const float nan = quiet_nan();
+            rvecs[hyp * 3 + 0] = nan, rvecs[hyp * 3 + 1] = nan, rvecs[hyp * 3 + 2] = nan;
+            tvecs[hyp * 3 + 0] = nan, tvecs[hyp * 3 + 1] = nan, tvecs[hyp * 3 + 2] = nan;
+        }
+        return;
+    }
+    if (slot != best) return;
+    tvecs[hyp * 3 + 0] = P.t[0], tvecs[hyp * 3 + 1] = P.t[1], tvecs[hyp * 3 + 2] = P.t[2];
+    float R[3][3], rv[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k / 3][k % 3] = P.R[k];
+    rot::rotation_to_rvec(R, rv);
+    rvecs[hyp * 3 + 0] = rv[0], rvecs[hyp * 3 + 1] = rv[1], rvecs[hyp * 3 + 2] = rv[2];
+}
+
 // order-preserving finite filter of the hypotheses (reference: voldor/geometry.cpp:156-165) fused with the
 // rvec pre-scaling for mean-shift (geometry.cpp:191)
 __global__ void __launch_bounds__(1024)
@@ -380,6 +448,13 @@ int solve_batch_p3p_device(const float* d_p3s, const float* d_p2s, const int* d_
                            bool use_ap3p, cudaStream_t s) {
     const float4* u4 = global_draws().ensure(n_poses, s);
     if (!u4) return (int)cudaErrorMemoryAllocation;
+    static const bool legacy = getenv("VB_P3P_LEGACY") != nullptr;  // A/B timing during the transition
+    if (!use_ap3p && !legacy) {
+        k_solve_p3p_quad<0><<<VB_DIV_CEIL(n_poses * 4, kQuadBlock), kQuadBlock, 0, s>>>(
+            d_p2s, d_p3s, d_n_pts, n_pts_host, u4, fx, fy, cx, cy, d_rvecs, d_tvecs, n_poses);
+        VB_RETURN_IF_CUDA_ERROR();
+        return 0;
+    }
     const int nb = VB_DIV_CEIL(n_poses, 32);
     if (use_ap3p)
         k_solve_p3p<true><<<nb, 32, 0, s>>>(d_p2s, d_p3s, d_n_pts, n_pts_host, u4, fx, fy, cx, cy, d_rvecs, d_tvecs,
