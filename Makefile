@@ -8,8 +8,8 @@ OBJS := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
 HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard include/*.h)
 LIB := voldor_b200/libvoldor_b200.so
 
-.PHONY: all lib oracle clean
-all: lib oracle
+.PHONY: all lib oracle probes clean
+all: lib oracle probes
 
 lib: $(LIB)
 
@@ -22,6 +22,12 @@ $(LIB): $(OBJS)
 
 oracle:
 	$(MAKE) -C oracle all
+
+# test infrastructure: device build of the minimal solvers with run-time switchable contraction sites
+probes: tests/_build/libp3p_probe.so
+tests/_build/libp3p_probe.so: tests/p3p_device_probe.cu $(HDRS)
+	@mkdir -p tests/_build
+	$(NVCC) -O3 $(ARCH) -std=c++17 -shared -Xcompiler -fPIC -o $@ $<
 
 clean:
 	rm -rf build $(LIB)

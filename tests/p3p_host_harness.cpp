@@ -16,7 +16,7 @@
 
 namespace vb {
 namespace quad {
-unsigned vbq_twist_sites = kTwistSitesFused, vbq_ap3p_sites = 0;
+unsigned vbq_twist_sites = 0, vbq_ap3p_sites = 0;
 }
 }  // namespace vb
 
@@ -25,7 +25,12 @@ using namespace vb::quad;
 extern "C" {
 
 void harness_set_sites(int solver, unsigned mask) { (solver == 0 ? vbq_twist_sites : vbq_ap3p_sites) = mask; }
-unsigned harness_default_sites(int solver) { return solver == 0 ? kTwistSitesFused : 0u; }
+unsigned harness_default_sites(int solver) {
+#ifdef HAVE_AP3P_QUAD
+    if (solver == 1) return kAp3pSitesFused;
+#endif
+    return solver == 0 ? kTwistSitesFused : 0u;
+}
 
 // the reference sampler's indices: int(curand_uniform * n_pts), 4 per hypothesis (solve_batch_lambdatwist.cu:16-19)
 void harness_indices(int n_poses, int n_pts, int* idx4) {

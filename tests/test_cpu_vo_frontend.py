@@ -186,3 +186,42 @@ def test_sequence_with_the_cpu_port_as_solver_follows_the_ground_truth():
     for a, b in zip(T, T_gt):
         assert np.abs(a[:3, :3] - b[:3, :3]).max() < 3e-2
         assert np.linalg.norm(a[:3, 3] - b[:3, 3] * scale) < 0.1 * np.linalg.norm(T[-1][:3, 3])
+
+
+def test_covisibility_score_is_the_reference_formula():
+    """literal transcription of the scoring of slam_py/slam_utils.py:18-53 (visibility, histogram2d coverage, their
+    combination) against vo_frontend.eval_covisibility, including a case where the coverage term decides"""
+    from voldor_b200 import vo_frontend
+
+    def reference_score(depth, T, K, mask=None, stride=4):
+        h, w = depth.shape
+        Iy, Ix = np.mgrid[0:h:stride, 0:w:stride]
+        c2 = np.stack([Ix, Iy, np.ones_like(Ix)], axis=2).astype(np.float32).reshape(-1, 3)
+        c3 = (np.linalg.inv(K) @ c2.T).T * depth[::stride, ::stride].reshape(-1, 1)
+        if mask is not None:
+            c3 = c3[mask[::stride, ::stride].reshape(-1)]
+        c3 = (T[:3, :3] @ c3.T).T + T[:3, 3]
+        pr = (K @ c3.T).T
+        pr = pr[pr[:, 2] > 0]
+        pr = pr[:, :2] / pr[:, 2:3]
+        vis = (pr[:, 0] > 0) & (pr[:, 0] < w) & (pr[:, 1] > 0) & (pr[:, 1] < h)
+        vis = np.sum(vis) / ((w // stride) * (h // stride))
+        cov, _, _ = np.histogram2d(pr[:, 0], pr[:, 1], bins=(w // (2 * stride), h // (2 * stride)), range=((0, w), (0, h)))
+        cov = np.sum(cov > 0) / ((w // (2 * stride)) * (h // (2 * stride)))
+        return 2 * (vis * cov) / max(vis + cov, 1)
+
+    w, h = 160, 120
+    K = np.array([[128.0, 0, 80], [0, 128, 60], [0, 0, 1]])
+    rng = np.random.default_rng(0)
+    depth = (8 + rng.uniform(-1, 1, (h, w))).astype(np.float32)
+    for t, mask in (([0.0, 0, 0], None), ([2.5, 0.5, 1.0], None), ([0, 0, 4.0], depth > 8.0), ([6.0, 0, 0], None)):
+        T = np.eye(4)
+        T[:3, :3] = vo_frontend.rvec_to_matrix(np.array([0.02, -0.05, 0.01]))
+        T[:3, 3] = t
+        a, b = vo_frontend.eval_covisibility(depth, T, K, mask), reference_score(depth, T, K, mask)
+        assert abs(a - b) < 1e-6, (t, a, b)
+    # forward motion keeps everything in view but shrinks the covered area: the score must drop below the visibility
+    T = np.eye(4)
+    T[2, 3] = -4.0
+    s = vo_frontend.eval_covisibility(depth, T, K)
+    assert s < 0.9

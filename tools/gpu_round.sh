@@ -32,6 +32,27 @@ sanitize)
 sanitizebig)
   timeout 900 compute-sanitizer --tool memcheck --kernel-name kns=vb --print-limit 20 python tools/sanitize_target.py --big > $out/sanitizer_memcheck_big.log 2>&1
   echo "memcheck big rc=$?"; grep -E "ERROR SUMMARY|sanitize_target" $out/sanitizer_memcheck_big.log | tail -3 ;;
+golden)
+  python tests/make_golden.py > $out/make_golden.log 2>&1; tail -3 $out/make_golden.log ;;
+p3ptime)
+  # per-launch time of the hypothesis sampler, quad-lane vs one thread per hypothesis (legacy), 4-iteration C2 window
+  for v in quad legacy; do
+    if [ $v = legacy ]; then export VB_P3P_LEGACY=1; else unset VB_P3P_LEGACY; fi
+    ncu --metrics gpu__time_duration.sum --clock-control none -k regex:solve_p3p --csv --log-file $out/p3p_$v.csv python tools/profile_window.py --iters 4 > $out/p3p_$v.log 2>&1
+    python tools/summarize_launches.py $out/p3p_$v.csv | tail -4
+  done; unset VB_P3P_LEGACY ;;
+inflight)
+  for m in 4 6 8; do
+    python bench.py --steps 6 --warmup 3 --inflight $m --no-extras --no-cpu-baseline --no-parity > $out/bench_inflight$m.json 2> $out/bench_inflight$m.err
+    python - <<PY
+import json
+try:
+    l=json.loads(open("$out/bench_inflight$m.json").read().strip().splitlines()[-1])
+    print("inflight $m value", round(l["value"],1), "e2e", round(l["e2e"]["value"],1), "lat", l["latency"]["ms_per_window_in_flight"])
+except Exception as e:
+    print("inflight $m failed", e, open("$out/bench_inflight$m.err").read()[-1500:])
+PY
+  done ;;
 probe)
   tools/_build/tex_probe 27 > $out/tex_probe.json 2>&1; cat $out/tex_probe.json ;;
 launches)

@@ -19,16 +19,24 @@
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e_), __LINE__); return 2; } } while (0)
 
-constexpr int kVariants = 8;
+constexpr int kVariants = 16;
 static const char* kNames[kVariants] = {
-    "q=rint(c*256)-128, exact 4-term sum rounded once (RN)",
-    "q=rint(c*256)-128, exact 4-term sum truncated (RZ)",
-    "q=rint(c*256)-128, fp32 fma chain T00,T10,T01,T11",
-    "q=rint(c*256)-128, two-stage fp32 lerp (x then y) with fma",
-    "q=floor(c*256)-128, exact 4-term sum rounded once (RN)",
-    "q=rint((c-0.5)*256), exact 4-term sum rounded once (RN)",
-    "q=rint(c*256)-128, two-stage lerp in double, rounded once",
-    "q=rint(c*256)-128, fp32 (1-a)*(1-b)*T.. products summed left to right",
+    "8 fraction bits (the documented 1.8 fixed point), exact 4-term sum rounded once",
+    "8 fraction bits, two-stage fp32 lerp (x then y) with fma",
+    "9 fraction bits, exact sum rounded once",
+    "10 fraction bits, exact sum rounded once",
+    "12 fraction bits, exact sum rounded once",
+    "16 fraction bits, exact sum rounded once",
+    "full fp32 fractions a=c-0.5-floor(c-0.5), exact sum rounded once",
+    "full fp32 fractions, two-stage fp32 lerp with fma: t=fma(a,T10-T00,T00)",
+    "full fp32 fractions, two-stage fp32 lerp: t=fma(a,T10,fma(-a,T00,T00))",
+    "full fp32 fractions, fp32 weights (1-a)(1-b).. fma chain",
+    "9 fraction bits, two-stage fp32 lerp with fma",
+    "10 fraction bits, two-stage fp32 lerp with fma",
+    "12 fraction bits, two-stage fp32 lerp with fma",
+    "16 fraction bits, two-stage fp32 lerp with fma",
+    "23 fraction bits (rint(c*2^23)), exact sum rounded once",
+    "8 fraction bits truncated (floor), two-stage fp32 lerp with fma",
 };
 
 struct Probe {
@@ -49,40 +57,39 @@ __device__ __forceinline__ float2 texel(const Probe& P, int x, int y) {
 }
 
 __device__ float emulate(int variant, const Probe& P, float cx, float cy, int comp) {
-    long qx, qy;
-    if (variant == 4) {
-        qx = (long)floorf(cx * 256.f) - 128, qy = (long)floorf(cy * 256.f) - 128;
-    } else if (variant == 5) {
-        qx = (long)rintf((cx - 0.5f) * 256.f), qy = (long)rintf((cy - 0.5f) * 256.f);
+    static const int kBits[kVariants] = {8, 8, 9, 10, 12, 16, 0, 0, 0, 0, 9, 10, 12, 16, 23, -8};
+    static const int kForm[kVariants] = {0, 1, 0, 0, 0, 0, 0, 1, 2, 3, 1, 1, 1, 1, 0, 1};
+    const int bits = kBits[variant], form = kForm[variant];
+    int ix, iy;
+    float a, b;
+    if (bits == 0) {
+        const float bx = cx - 0.5f, by = cy - 0.5f;
+        const float fxl = floorf(bx), fyl = floorf(by);
+        ix = (int)fxl, iy = (int)fyl;
+        a = bx - fxl, b = by - fyl;
     } else {
-        qx = (long)rintf(cx * 256.f) - 128, qy = (long)rintf(cy * 256.f) - 128;
+        const int nb = bits < 0 ? -bits : bits;
+        const double sc = (double)(1ll << nb);
+        const long long qx = (bits < 0 ? (long long)floor((double)cx * sc) : (long long)rint((double)cx * sc)) - (1ll << (nb - 1));
+        const long long qy = (bits < 0 ? (long long)floor((double)cy * sc) : (long long)rint((double)cy * sc)) - (1ll << (nb - 1));
+        ix = (int)(qx >> nb), iy = (int)(qy >> nb);
+        a = (float)((double)(qx & ((1ll << nb) - 1)) / sc), b = (float)((double)(qy & ((1ll << nb) - 1)) / sc);
     }
-    const int ix = (int)(qx >> 8), iy = (int)(qy >> 8);
-    const float a = (float)(qx & 255) * (1.f / 256.f), b = (float)(qy & 255) * (1.f / 256.f);
     const float2 t00 = texel(P, ix, iy), t10 = texel(P, ix + 1, iy), t01 = texel(P, ix, iy + 1), t11 = texel(P, ix + 1, iy + 1);
     const float v00 = comp ? t00.y : t00.x, v10 = comp ? t10.y : t10.x, v01 = comp ? t01.y : t01.x, v11 = comp ? t11.y : t11.x;
-    const float w00 = (1.f - a) * (1.f - b), w10 = a * (1.f - b), w01 = (1.f - a) * b, w11 = a * b;  // exact in fp32
-    switch (variant) {
-        case 0: case 4: case 5: {
-            const double s = (double)w00 * v00 + (double)w10 * v10 + (double)w01 * v01 + (double)w11 * v11;
-            return __double2float_rn(s);
-        }
-        case 1: {
-            const double s = (double)w00 * v00 + (double)w10 * v10 + (double)w01 * v01 + (double)w11 * v11;
-            return __double2float_rz(s);
-        }
-        case 2: return __fmaf_rn(w11, v11, __fmaf_rn(w01, v01, __fmaf_rn(w10, v10, __fmul_rn(w00, v00))));
-        case 3: {
-            const float top = __fmaf_rn(a, __fsub_rn(v10, v00), v00), bot = __fmaf_rn(a, __fsub_rn(v11, v01), v01);
-            return __fmaf_rn(b, __fsub_rn(bot, top), top);
-        }
-        case 6: {
-            const double top = (double)v00 + (double)a * ((double)v10 - (double)v00);
-            const double bot = (double)v01 + (double)a * ((double)v11 - (double)v01);
-            return __double2float_rn(top + (double)b * (bot - top));
-        }
-        default:
-            return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w00, v00), __fmul_rn(w10, v10)), __fmul_rn(w01, v01)), __fmul_rn(w11, v11));
+    if (form == 0) {
+        const double da = a, db = b;
+        const double s = (1 - da) * (1 - db) * v00 + da * (1 - db) * v10 + (1 - da) * db * v01 + da * db * v11;
+        return __double2float_rn(s);
+    } else if (form == 1) {
+        const float top = __fmaf_rn(a, __fsub_rn(v10, v00), v00), bot = __fmaf_rn(a, __fsub_rn(v11, v01), v01);
+        return __fmaf_rn(b, __fsub_rn(bot, top), top);
+    } else if (form == 2) {
+        const float top = __fmaf_rn(a, v10, __fmaf_rn(-a, v00, v00)), bot = __fmaf_rn(a, v11, __fmaf_rn(-a, v01, v01));
+        return __fmaf_rn(b, bot, __fmaf_rn(-b, top, top));
+    } else {
+        const float w00 = __fmul_rn(1.f - a, 1.f - b), w10 = __fmul_rn(a, 1.f - b), w01 = __fmul_rn(1.f - a, b), w11 = __fmul_rn(a, b);
+        return __fmaf_rn(w11, v11, __fmaf_rn(w01, v01, __fmaf_rn(w10, v10, __fmul_rn(w00, v00))));
     }
 }
 

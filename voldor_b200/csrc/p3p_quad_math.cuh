@@ -78,12 +78,16 @@ struct Pose {
 // Sites where the reference's PTX leaves a multi-use product next to an add/sub, so that reading the PTX does not
 // settle whether ptxas folded a copy of the product into an FFMA.  Each site is one bit of a per-solver mask; the
 // values were fixed by exhaustive search against golden hypotheses of the reference kernels
-// (tests/test_cpu_p3p_quad.py: the only assignment reproducing every hypothesis bit for bit).  The host test build
+// (tests/test_cpu_p3p_quad.py on the host, tests/test_gpu_p3p_sites.py on the device: the only assignment reproducing
+// every hypothesis bit for bit).  The host test build
 // (-DVBQ_SITE_SEARCH) can override the masks at run time to repeat that search.
 #if !defined(__CUDACC__) && defined(VBQ_SITE_SEARCH)
 extern unsigned vbq_twist_sites, vbq_ap3p_sites;
 #define VBQ_TWIST_SITE(bit) ((vbq_twist_sites >> (bit)) & 1u)
 #define VBQ_AP3P_SITE(bit) ((vbq_ap3p_sites >> (bit)) & 1u)
+#elif defined(VBQ_SITE_SEARCH_DEVICE)  // tests/p3p_device_probe.cu: masks in __constant__ memory declared by the includer
+#define VBQ_TWIST_SITE(bit) ((c_twist_sites >> (bit)) & 1u)
+#define VBQ_AP3P_SITE(bit) ((c_ap3p_sites >> (bit)) & 1u)
 #else
 #define VBQ_TWIST_SITE(bit) ((kTwistSitesFused >> (bit)) & 1u)
 #define VBQ_AP3P_SITE(bit) ((kAp3pSitesFused >> (bit)) & 1u)
@@ -93,6 +97,30 @@ extern unsigned vbq_twist_sites, vbq_ap3p_sites;
 VBQ_FN float site_addmul(unsigned fused, float c, float a, float b, bool negate_product) {
     if (fused) return fma(negate_product ? -a : a, b, c);
     return negate_product ? sub(c, mul(a, b)) : add(c, mul(a, b));
+}
+
+// squared pixel distance between the projection of X under P and the observation (lambdatwist_p4p.h:30-37, solve_batch_ap3p.cu:362-369)
+VBQ_FN float reprojection_error(const Pose& P, const Vec3f& X, float u, float v, float fx, float fy, float cx,
+                                float cy) {
+    const float px = add(fma(P.R[2], X.z, fma(P.R[0], X.x, mul(P.R[1], X.y))), P.t[0]);
+    const float py = add(fma(P.R[5], X.z, fma(P.R[3], X.x, mul(P.R[4], X.y))), P.t[1]);
+    const float pz = add(fma(P.R[8], X.z, fma(P.R[6], X.x, mul(P.R[7], X.y))), P.t[2]);
+    const float du = sub(add(cx, quot(mul(fx, px), pz)), u);
+    const float dv = sub(add(cy, quot(mul(fy, py), pz)), v);
+    return fma(du, du, mul(dv, dv));
+}
+
+// The reference's scan over the (compacted) candidate list, on the four (exists, error) pairs in slot order: the
+// first existing candidate is taken, a later one replaces it only when strictly better (NaN never replaces).
+// Returns the winning slot or -1.
+VBQ_FN int pick_by_fourth_point(const bool exists[4], const float err[4]) {
+    int best = -1;
+    float best_err = 0.f;
+    for (int q = 0; q < 4; ++q) {
+        if (!exists[q]) continue;
+        if (best < 0 || best_err > err[q]) best = q, best_err = err[q];
+    }
+    return best;
 }
 
 }  // namespace quad

@@ -290,17 +290,6 @@ VBQ_FN void twist_pose(const TwistShared& S, const TriangleFrameInverse& Xi, con
     }
 }
 
-// squared pixel distance between the projection of X under P and the observation (lambdatwist_p4p.h:30-37)
-VBQ_FN float reprojection_error(const Pose& P, const Vec3f& X, float u, float v, float fx, float fy, float cx,
-                                float cy) {
-    const float px = add(fma(P.R[2], X.z, fma(P.R[0], X.x, mul(P.R[1], X.y))), P.t[0]);
-    const float py = add(fma(P.R[5], X.z, fma(P.R[3], X.x, mul(P.R[4], X.y))), P.t[1]);
-    const float pz = add(fma(P.R[8], X.z, fma(P.R[6], X.x, mul(P.R[7], X.y))), P.t[2]);
-    const float du = sub(add(cx, quot(mul(fx, px), pz)), u);
-    const float dv = sub(add(cy, quot(mul(fy, py), pz)), v);
-    return fma(du, du, mul(dv, dv));
-}
-
 // everything lane `slot` does for one hypothesis: returns whether its candidate exists; pose + error if it does
 VBQ_FN bool twist_lane(int slot, const float* uv /*[4][2]*/, const Vec3f* X /*[4]*/, float fx, float fy, float cx,
                        float cy, Pose& P, float& err) {
@@ -315,19 +304,6 @@ VBQ_FN bool twist_lane(int slot, const float* uv /*[4][2]*/, const Vec3f* X /*[4
     twist_pose(S, Xi, X[0], l1, l2, l3, P);
     err = reprojection_error(P, X[3], uv[6], uv[7], fx, fy, cx, cy);
     return true;
-}
-
-// The reference's scan over the (compacted) candidate list, on the four (exists, error) pairs in slot order: the
-// first existing candidate is taken, a later one replaces it only when strictly better (NaN never replaces).
-// Returns the winning slot or -1.
-VBQ_FN int pick_by_fourth_point(const bool exists[4], const float err[4]) {
-    int best = -1;
-    float best_err = 0.f;
-    for (int q = 0; q < 4; ++q) {
-        if (!exists[q]) continue;
-        if (best < 0 || best_err > err[q]) best = q, best_err = err[q];
-    }
-    return best;
 }
 
 }  // namespace quad

@@ -5,6 +5,7 @@
 #include "p3p_lambdatwist.cuh"
 #include "p3p_ap3p.cuh"
 #include "p3p_twist_quad.cuh"
+#include "p3p_ap3p_quad.cuh"
 #include "rotation.cuh"
 #include <curand_kernel.h>
 #include <algorithm>
@@ -292,7 +293,8 @@ __global__ void __launch_bounds__(kQuadBlock)
             X[k].z = __shfl_sync(qmask, pz, qbase + k);
         }
         float err = 0.f;
-        const bool mine_exists = quad::twist_lane(slot, uv, X, fx, fy, cx, cy, P, err);
+        const bool mine_exists = SOLVER == 0 ? quad::twist_lane(slot, uv, X, fx, fy, cx, cy, P, err)
+                                             : quad::ap3p_lane(slot, uv, X, fx, fy, cx, cy, P, err);
         bool exists[4];
         float errs[4];
 #pragma unroll
@@ -449,9 +451,14 @@ int solve_batch_p3p_device(const float* d_p3s, const float* d_p2s, const int* d_
     const float4* u4 = global_draws().ensure(n_poses, s);
     if (!u4) return (int)cudaErrorMemoryAllocation;
     static const bool legacy = getenv("VB_P3P_LEGACY") != nullptr;  // A/B timing during the transition
-    if (!use_ap3p && !legacy) {
-        k_solve_p3p_quad<0><<<VB_DIV_CEIL(n_poses * 4, kQuadBlock), kQuadBlock, 0, s>>>(
-            d_p2s, d_p3s, d_n_pts, n_pts_host, u4, fx, fy, cx, cy, d_rvecs, d_tvecs, n_poses);
+    if (!legacy) {
+        const int nb = VB_DIV_CEIL(n_poses * 4, kQuadBlock);
+        if (use_ap3p)
+            k_solve_p3p_quad<1><<<nb, kQuadBlock, 0, s>>>(d_p2s, d_p3s, d_n_pts, n_pts_host, u4, fx, fy, cx, cy, d_rvecs,
+                                                         d_tvecs, n_poses);
+        else
+            k_solve_p3p_quad<0><<<nb, kQuadBlock, 0, s>>>(d_p2s, d_p3s, d_n_pts, n_pts_host, u4, fx, fy, cx, cy, d_rvecs,
+                                                         d_tvecs, n_poses);
         VB_RETURN_IF_CUDA_ERROR();
         return 0;
     }

@@ -56,7 +56,11 @@ def polish_T44(T):
 
 
 def eval_covisibility(depth, Tc1c2, K, mask=None, stride=4):
-    """fraction of the (strided) pixels of a depth map that stay in view after Tc1c2 (slam_utils.py:18-49)"""
+    """covisibility score of a depth map after the motion Tc1c2 (slam_utils.py:18-53): harmonic-style combination
+    2*v*c / max(v + c, 1) of the fraction v of the (strided) pixels that stay in view and the fraction c of the
+    (w/2stride x h/2stride) image cells they cover.  Deviation from the reference, on purpose: K here is the intrinsic
+    matrix AFTER the flow rescale (the reference builds it from the unscaled fx, fy, voldor_slam.py:175,495), which only
+    matters when rescale != 1."""
     h, w = depth.shape
     Iy, Ix = np.mgrid[0:h:stride, 0:w:stride]
     rays = (np.linalg.inv(K) @ np.stack([Ix, Iy, np.ones_like(Ix)], 2).reshape(-1, 3).astype(np.float64).T).T
@@ -68,7 +72,11 @@ def eval_covisibility(depth, Tc1c2, K, mask=None, stride=4):
     p = p[p[:, 2] > 0]
     p = p[:, :2] / p[:, 2:3]
     vis = (p[:, 0] > 0) & (p[:, 0] < w) & (p[:, 1] > 0) & (p[:, 1] < h)
-    return vis.sum() / ((w // stride) * (h // stride))
+    visibility = vis.sum() / ((w // stride) * (h // stride))
+    bins = (w // (2 * stride), h // (2 * stride))
+    cells, _, _ = np.histogram2d(p[:, 0], p[:, 1], bins=bins, range=((0, w), (0, h)))
+    coverage = np.sum(cells > 0) / (bins[0] * bins[1])
+    return 2 * (visibility * coverage) / max(visibility + coverage, 1)
 
 
 def huber_slope(x, y, epsilon=1.35, iters=30):
