@@ -24,7 +24,10 @@ oracle:
 	$(MAKE) -C oracle all
 
 # test infrastructure: device build of the minimal solvers with run-time switchable contraction sites
-probes: tests/_build/libp3p_probe.so
+probes: tests/_build/libp3p_probe.so tests/_build/libpow_probe.so
+tests/_build/libpow_probe.so: tests/pow_device_probe.cu $(HDRS)
+	@mkdir -p tests/_build
+	$(NVCC) -O3 $(ARCH) -std=c++17 -shared -Xcompiler -fPIC -o $@ $<
 tests/_build/libp3p_probe.so: tests/p3p_device_probe.cu $(HDRS)
 	@mkdir -p tests/_build
 	$(NVCC) -O3 $(ARCH) -std=c++17 -shared -Xcompiler -fPIC -o $@ $<

@@ -53,6 +53,14 @@ except Exception as e:
     print("inflight $m failed", e, open("$out/bench_inflight$m.err").read()[-1500:])
 PY
   done ;;
+weights)
+  tools/_build/tex_probe weights $out/tex_weights.bin > $out/tex_weights.json 2>&1; cat $out/tex_weights.json ;;
+tpl)
+  # local propagation: two likelihood terms per lane instead of one, several windows in flight
+  for t in 1 2; do
+    VB_LOCAL_TPL=$t python bench.py --steps 6 --warmup 3 --inflight 6 --no-extras --no-cpu-baseline --no-parity > $out/bench_tpl$t.json 2> $out/bench_tpl$t.err
+    python -c "import json;l=json.loads(open('$out/bench_tpl$t.json').read().strip().splitlines()[-1]);print('TPL $t inflight 6 value',round(l['value'],1),'single',round(l['latency']['single_window']['value'],1), 'search ms', round(l['roofline']['avg_launch_ms'],4))" || tail -5 $out/bench_tpl$t.err
+  done ;;
 probe)
   tools/_build/tex_probe 27 > $out/tex_probe.json 2>&1; cat $out/tex_probe.json ;;
 launches)

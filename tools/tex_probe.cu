@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstdint>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e_), __LINE__); return 2; } } while (0)
@@ -135,7 +136,57 @@ __global__ void k_probe(Probe P, int h, unsigned long long n, unsigned long long
         if (local[v]) atomicAdd(&mismatches[v], local[v]);
 }
 
+// ---- weight sweep: read the filter weight the hardware applies as a function of the coordinate -------------------
+// texels are 0 everywhere except one column (x sweep) / one row (y sweep) of ones, so a fetch half a texel around it
+// returns the weight itself.
+__global__ void k_weights(cudaTextureObject_t tex, float x0, float y0, int n, float* out_x, float* out_y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float d = (float)i / (float)n;  // [0, 1)
+    out_x[i] = tex2D<float2>(tex, x0 + d, y0).x;   // alpha(x)
+    out_y[i] = tex2D<float2>(tex, x0, y0 + d).y;   // beta(y)
+}
+static int weight_sweep(const char* path) {
+    const int w = 256, H = 256, n = 1 << 16;
+    float2* d = nullptr;
+    size_t pitch = 0;
+    CK(cudaMallocPitch((void**)&d, &pitch, (size_t)w * sizeof(float2), (size_t)H));
+    std::vector<float2> host((size_t)w * H, make_float2(0.f, 0.f));
+    for (int y = 0; y < H; y++) host[(size_t)y * w + 101].x = 1.f;  // column of ones in .x
+    for (int x = 0; x < w; x++) host[(size_t)51 * w + x].y = 1.f;   // row of ones in .y
+    CK(cudaMemcpy2D(d, pitch, host.data(), (size_t)w * sizeof(float2), (size_t)w * sizeof(float2), H, cudaMemcpyHostToDevice));
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypePitch2D;
+    rd.res.pitch2D.desc = cudaCreateChannelDesc<float2>();
+    rd.res.pitch2D.devPtr = d, rd.res.pitch2D.width = w, rd.res.pitch2D.height = H, rd.res.pitch2D.pitchInBytes = pitch;
+    cudaTextureDesc td = {};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear, td.readMode = cudaReadModeElementType, td.normalizedCoords = 0;
+    cudaTextureObject_t tex;
+    CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+    float *ox, *oy;
+    CK(cudaMalloc((void**)&ox, n * sizeof(float)));
+    CK(cudaMalloc((void**)&oy, n * sizeof(float)));
+    // texel 100 has its centre at 100.5: sweeping the coordinate over [100.5, 101.5) moves the weight of texel 101 over [0, 1)
+    k_weights<<<(n + 255) / 256, 256>>>(tex, 100.5f, 50.5f, n, ox, oy);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> hx(n), hy(n);
+    CK(cudaMemcpy(hx.data(), ox, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hy.data(), oy, n * sizeof(float), cudaMemcpyDeviceToHost));
+    FILE* f = fopen(path, "wb");
+    if (!f) return 3;
+    fwrite(hx.data(), sizeof(float), n, f);
+    fwrite(hy.data(), sizeof(float), n, f);
+    fclose(f);
+    int steps = 0;
+    for (int i = 1; i < n; i++) steps += hx[i] != hx[i - 1];
+    printf("{\"weight_sweep\": \"%s\", \"samples\": %d, \"distinct_steps_x\": %d, \"alpha_at_0\": %.9g, \"alpha_at_quarter\": %.9g, \"alpha_last\": %.9g}\n",
+           path, n, steps, hx[0], hx[n / 4], hx[n - 1]);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 2 && !strcmp(argv[1], "weights")) return weight_sweep(argv[2]);
     const int lg = argc > 1 ? atoi(argv[1]) : 27;
     const unsigned long long n = 1ull << lg;
     const int w = 640, h = 480, layers = 8, H = h * layers;

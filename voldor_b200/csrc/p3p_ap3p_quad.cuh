@@ -36,8 +36,9 @@ enum Ap3pSite {
     kSiteG1SqInC2 = 8,      // c2 = ... - g1*g1      (the product also feeds an fma as addend)
     kSiteG2SqInC2 = 9       // c2 = g2*g2 + ...      (likewise)
 };
-// products whose consumers are all add/sub of the same block are folded into them, the others stay rounded
-constexpr unsigned kAp3pSitesFused = 0xFFu;
+// g3*g3, g4*g3 and g4*g4 are folded into both of their consumers; every other site keeps its rounded product
+// (search over all 2^10 assignments on the device against 8192 hypotheses of the reference kernel)
+constexpr unsigned kAp3pSitesFused = 0x3Fu;
 
 #if defined(__CUDA_ARCH__)
 VBQ_FN float lib_cbrt(float a) { return cbrtf(a); }
