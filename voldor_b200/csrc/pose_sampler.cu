@@ -2,8 +2,6 @@
 // See pose_sampler.cuh for the reference call sites this replaces.
 #include "pose_sampler.cuh"
 #include "geometry.cuh"
-#include "p3p_lambdatwist.cuh"
-#include "p3p_ap3p.cuh"
 #include "p3p_twist_quad.cuh"
 #include "p3p_ap3p_quad.cuh"
 #include "rotation.cuh"
@@ -213,47 +211,6 @@ __global__ void k_hypothesis_draws(float4* u4, int n) {
     u4[idx] = u;
 }
 
-// one thread = one hypothesis (reference: solve_batch_lambdatwist.cu:11-42, solve_batch_ap3p.cu:331-378)
-template <bool AP3P>
-__global__ void __launch_bounds__(32)
-    k_solve_p3p(const float* __restrict__ p2s, const float* __restrict__ p3s, const int* d_n_pts, int n_pts_host,
-                const float4* __restrict__ u4, float fx, float fy, float cx, float cy, float* rvecs, float* tvecs,
-                int n_poses) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_poses) return;
-    const int n_pts = d_n_pts ? *d_n_pts : n_pts_host;
-    bool success = false;
-    float R[3][3], t[3];
-    if (n_pts >= 4 || !d_n_pts) {
-        const float4 u = u4[idx];
-        const float fn = (float)n_pts;
-        const int i1 = (int)f_mul(u.x, fn);  // can equal n_pts when u == 1; buffers are padded
-        const int i2 = (int)f_mul(u.y, fn);
-        const int i3 = (int)f_mul(u.z, fn);
-        const int i4 = (int)f_mul(u.w, fn);
-        if (AP3P)
-            success = ap3p::p4p_solve(&p2s[i1 * 2], &p2s[i2 * 2], &p2s[i3 * 2], &p2s[i4 * 2], &p3s[i1 * 3],
-                                      &p3s[i2 * 3], &p3s[i3 * 3], &p3s[i4 * 3], fx, fy, cx, cy, R, t);
-        else
-            success = p3p::p4p_solve(&p2s[i1 * 2], &p2s[i2 * 2], &p2s[i3 * 2], &p2s[i4 * 2], &p3s[i1 * 3],
-                                     &p3s[i2 * 3], &p3s[i3 * 3], &p3s[i4 * 3], fx, fy, cx, cy, R, t);
-    }
-    if (!success) {
-        const float nan = quiet_nan();
-        rvecs[idx * 3 + 0] = nan, rvecs[idx * 3 + 1] = nan, rvecs[idx * 3 + 2] = nan;
-        tvecs[idx * 3 + 0] = nan, tvecs[idx * 3 + 1] = nan, tvecs[idx * 3 + 2] = nan;
-        return;
-    }
-    tvecs[idx * 3 + 0] = t[0];
-    tvecs[idx * 3 + 1] = t[1];
-    tvecs[idx * 3 + 2] = t[2];
-    float rv[3];
-    rot::rotation_to_rvec(R, rv);
-    rvecs[idx * 3 + 0] = rv[0];
-    rvecs[idx * 3 + 1] = rv[1];
-    rvecs[idx * 3 + 2] = rv[2];
-}
-
 // ------------------------------------------------------------------------------------------------
 // Quad-lane sampler: four consecutive lanes share one hypothesis (p3p_twist_quad.cuh).  Lane q of a quad fetches the
 // q-th sampled correspondence (one gather per point instead of every thread gathering all four), the quad exchanges
@@ -450,25 +407,13 @@ int solve_batch_p3p_device(const float* d_p3s, const float* d_p2s, const int* d_
                            bool use_ap3p, cudaStream_t s) {
     const float4* u4 = global_draws().ensure(n_poses, s);
     if (!u4) return (int)cudaErrorMemoryAllocation;
-    static const bool legacy = getenv("VB_P3P_LEGACY") != nullptr;  // A/B timing during the transition
-    if (!legacy) {
-        const int nb = VB_DIV_CEIL(n_poses * 4, kQuadBlock);
-        if (use_ap3p)
-            k_solve_p3p_quad<1><<<nb, kQuadBlock, 0, s>>>(d_p2s, d_p3s, d_n_pts, n_pts_host, u4, fx, fy, cx, cy, d_rvecs,
-                                                         d_tvecs, n_poses);
-        else
-            k_solve_p3p_quad<0><<<nb, kQuadBlock, 0, s>>>(d_p2s, d_p3s, d_n_pts, n_pts_host, u4, fx, fy, cx, cy, d_rvecs,
-                                                         d_tvecs, n_poses);
-        VB_RETURN_IF_CUDA_ERROR();
-        return 0;
-    }
-    const int nb = VB_DIV_CEIL(n_poses, 32);
+    const int nb = VB_DIV_CEIL(n_poses * 4, kQuadBlock);
     if (use_ap3p)
-        k_solve_p3p<true><<<nb, 32, 0, s>>>(d_p2s, d_p3s, d_n_pts, n_pts_host, u4, fx, fy, cx, cy, d_rvecs, d_tvecs,
-                                            n_poses);
+        k_solve_p3p_quad<1><<<nb, kQuadBlock, 0, s>>>(d_p2s, d_p3s, d_n_pts, n_pts_host, u4, fx, fy, cx, cy, d_rvecs,
+                                                     d_tvecs, n_poses);
     else
-        k_solve_p3p<false><<<nb, 32, 0, s>>>(d_p2s, d_p3s, d_n_pts, n_pts_host, u4, fx, fy, cx, cy, d_rvecs, d_tvecs,
-                                             n_poses);
+        k_solve_p3p_quad<0><<<nb, kQuadBlock, 0, s>>>(d_p2s, d_p3s, d_n_pts, n_pts_host, u4, fx, fy, cx, cy, d_rvecs,
+                                                     d_tvecs, n_poses);
     VB_RETURN_IF_CUDA_ERROR();
     return 0;
 }
