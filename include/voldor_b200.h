@@ -53,6 +53,13 @@ int vb_align_frame_init_gpu(float** h_images, float** h_depths, float** h_weight
 int vb_align_frame_eval_gpu(int ref_fid, int tar_fid, const float* h_params_ref, const float* h_params_tar,
                             float* h_o_residual, float* h_o_jacobian, int apply_weights);
 
+/* No counterpart in the reference ABI: the same evaluation restricted to the samples its only caller reads — every
+ * stride-th pixel in x and y (frame-alignment/align_frame_cost_fun.h:183-229), packed as
+ * out[(y/stride) * ceil(w/stride) + x/stride] (x9 for the Jacobian).  stride 16 cuts the per-evaluation D2H from
+ * 40 B/px to 40/256 B/px.  Values are those of vb_align_frame_eval_gpu at the same pixels. */
+int vb_align_frame_eval_strided(int ref_fid, int tar_fid, const float* h_params_ref, const float* h_params_tar,
+                                float* h_o_residual, float* h_o_jacobian, int apply_weights, int stride);
+
 /* reference: gpu-kernels/gblur.h:6 (gblur.cu:47-72; device-to-device in the reference, host buffers here).
  * src/dst: [depth][h][w] float, ksize odd. */
 int vb_gblur_gpu(const float* h_src, float* h_dst, int w, int h, int depth, float sigma, int ksize);

@@ -307,6 +307,33 @@ def test_gblur_rejects_oversized_kernel(libs):
     assert rc1 == rc2 != 0
 
 
+def test_align_frame_strided_output_equals_the_full_evaluation(libs):
+    """packed every-stride-th-sample mode (what frame-alignment/align_frame_cost_fun.h:183-229 consumes) against the
+    full evaluation of the reference kernels subsampled on the host the way the cost function does it"""
+    import ctypes as C
+    mine, ref = libs
+    w, h, N = 100, 70, 3
+    win, images, depths, weights = _align_inputs(w, h, N, 17)
+    p_ref = np.array([0.01, -0.02, 0.005, 0.05, 0.02, 0.1, 0.01, 0.02, -0.01], np.float32)
+    p_tar = np.array([-0.005, 0.01, 0.0, 0.0, 0.01, -0.05, 0.0, -0.01, 0.02], np.float32)
+    assert mine.align_init(images, depths, weights, win["K"], 40.0, 0.5) == 0
+    rc, res_full, jac_full = mine.align_eval(0, 1, p_ref, p_tar, w, h, True)
+    assert rc == 0
+    f = mine.lib.vb_align_frame_eval_strided
+    f.argtypes = [C.c_int, C.c_int, ffi.FP, ffi.FP, ffi.FP, ffi.FP, C.c_int, C.c_int]
+    for stride in (1, 4, 16):
+        ow, oh = -(-w // stride), -(-h // stride)
+        res = np.full((oh, ow), -7, np.float32)
+        jac = np.full((oh, ow, 9), -7, np.float32)
+        assert f(0, 1, ffi._fp(p_ref), ffi._fp(p_tar), ffi._fp(res), ffi._fp(jac), 1, stride) == 0
+        assert ffi.bits_equal(res, res_full[::stride, ::stride])
+        assert ffi.bits_equal(jac, jac_full[::stride, ::stride])
+    # and the full evaluation itself is the reference's (tolerance level, see test_align_frame_parity)
+    assert ref.align_init(images, depths, weights, win["K"], 40.0, 0.5) == 0
+    rc, res_r, jac_r = ref.align_eval(0, 1, p_ref, p_tar, w, h, True)
+    assert np.array_equal(np.isnan(res_r), np.isnan(res_full))
+
+
 def test_rvec_to_matrix_identical_on_host_and_device():
     """the pipelined camera loop converts poses on the device, the oracle orchestration on the host: same source,
     every operation individually rounded, own sin/cos -> identical bits (csrc/host_math.h)"""

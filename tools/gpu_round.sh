@@ -61,6 +61,28 @@ tpl)
     VB_LOCAL_TPL=$t python bench.py --steps 6 --warmup 3 --inflight 6 --no-extras --no-cpu-baseline --no-parity > $out/bench_tpl$t.json 2> $out/bench_tpl$t.err
     python -c "import json;l=json.loads(open('$out/bench_tpl$t.json').read().strip().splitlines()[-1]);print('TPL $t inflight 6 value',round(l['value'],1),'single',round(l['latency']['single_window']['value'],1), 'search ms', round(l['roofline']['avg_launch_ms'],4))" || tail -5 $out/bench_tpl$t.err
   done ;;
+profile)
+  # (1) top kernels, full sections, one launch each (one window of the benchmarked shape); raw + source pages are
+  #     exported on the box, only the search-kernel report itself travels back (gpurun_out/ is capped at 64 MiB)
+  ncu --set full --clock-control none --import-source on -k regex:k_cost_and_random_search -s 1 -c 1 -f -o $out/search python tools/profile_window.py --iters 3 > $out/ncu_search.log 2>&1
+  ncu --set full --clock-control none -k regex:k_local_propagation_group -s 4 -c 4 -f -o $out/localprop python tools/profile_window.py --iters 3 > $out/ncu_local.log 2>&1
+  ncu --set full --clock-control none -k regex:k_solve_p3p_quad -s 8 -c 1 -f -o $out/p3p_quad python tools/profile_window.py --iters 3 > $out/ncu_p3p.log 2>&1
+  ncu --set full --clock-control none -k regex:k_update_rigidness -s 1 -c 1 -f -o $out/estep python tools/profile_window.py --iters 3 > $out/ncu_estep.log 2>&1
+  for r in search localprop p3p_quad estep; do
+    ncu -i $out/$r.ncu-rep --page raw --csv > $out/${r}_raw.csv 2>/dev/null
+  done
+  ncu -i $out/search.ncu-rep --page source --csv > $out/search_source.csv 2>/dev/null
+  rm -f $out/localprop.ncu-rep $out/p3p_quad.ncu-rep $out/estep.ncu-rep
+  ls -la $out/*.ncu-rep $out/*_raw.csv
+  # (2) every launch of one full 30-iteration window: duration + executed warp instructions
+  ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none --csv --log-file $out/window_launches.csv python tools/profile_window.py --iters 30 > $out/ncu_window.log 2>&1
+  echo "window launches rc=$?"; wc -l $out/window_launches.csv
+  # (3) launch list of the bench command itself
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file $out/launches_bench.csv python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline --no-parity > $out/bench_under_ncu.log 2>&1
+  echo "bench launches rc=$?"; wc -l $out/launches_bench.csv ;;
+gpus2)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 4 --warmup 3 --no-extras --no-cpu-baseline > $out/bench_gpus2.json 2> $out/bench_gpus2.err
+  tail -c 1500 $out/bench_gpus2.json; tail -3 $out/bench_gpus2.err ;;
 probe)
   tools/_build/tex_probe 27 > $out/tex_probe.json 2>&1; cat $out/tex_probe.json ;;
 launches)

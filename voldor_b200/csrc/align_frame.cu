@@ -197,11 +197,15 @@ struct AlignParams {
 // residual + Jacobian + weighted sqrt-Cauchy loss, one thread per reference pixel (align_frame.cu:205-411)
 __global__ void __launch_bounds__(128)
     k_align_eval(AlignView A, const AlignParams P, int f_ref, int f_tar, int photo, int with_jacobian,
-                 int apply_weights) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+                 int apply_weights, int stride) {
+    // stride 1: every pixel, outputs at (y, x).  stride s > 1: only the pixels the reference's cost function reads
+    // (x % s == 0, y % s == 0; frame-alignment/align_frame_cost_fun.h:183-185), outputs packed at
+    // (y/s) * ceil(w/s) + x/s.  The per-pixel arithmetic does not depend on the mode.
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gy = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = gx * stride, y = gy * stride;
     if (x >= A.w || y >= A.h) return;
-    const size_t pix = (size_t)y * A.w + x;
+    const size_t pix = stride == 1 ? (size_t)y * A.w + x : (size_t)gy * ((A.w + stride - 1) / stride) + gx;
     float* jac = A.jacobian + pix * kAlignParams;
     float J[kAlignParams];
     for (int i = 0; i < kAlignParams; i++) J[i] = 0.f;
@@ -393,12 +397,44 @@ int align_frame_eval_gpu(int ref_fid, int tar_fid, const float* h_params_ref, co
     memcpy(P.tar, S.params_tar, sizeof(P.tar));
     const dim3 b(32, 4), g(VB_DIV_CEIL(S.w, 32), VB_DIV_CEIL(S.h, 4));
     k_align_eval<<<g, b, 0, s>>>(make_view(S), P, ref_fid, tar_fid, S.photo ? 1 : 0, h_o_jacobian != nullptr,
-                                 apply_weights ? 1 : 0);
+                                 apply_weights ? 1 : 0, 1);
     VB_RETURN_IF_CUDA_ERROR();
     const size_t npx = (size_t)S.w * S.h;
     if (h_o_residual) VB_CUDA(cudaMemcpyAsync(h_o_residual, S.residual, npx * sizeof(float), cudaMemcpyDefault, s));
     if (h_o_jacobian)
         VB_CUDA(cudaMemcpyAsync(h_o_jacobian, S.jacobian, npx * kAlignParams * sizeof(float), cudaMemcpyDefault, s));
+    VB_CUDA(cudaStreamSynchronize(s));
+    VB_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+// Strided / packed evaluation: what the only caller of align_frame_eval_gpu actually consumes.  The reference's cost
+// function downloads the full residual (4 B/px) and Jacobian (36 B/px) of every evaluation and then reads every
+// `stride`-th sample of both (frame-alignment/align_frame_cost_fun.h:169-229, stride 16 in practice); here only those
+// samples are computed and copied: ceil(h/stride) x ceil(w/stride) residuals and 9x as many Jacobian entries, in the
+// cost function's own index order.  Same per-pixel arithmetic as the full evaluation.
+static int align_frame_eval_strided(int ref_fid, int tar_fid, const float* h_params_ref, const float* h_params_tar,
+                                    float* h_o_residual, float* h_o_jacobian, bool apply_weights, int stride) {
+    using namespace vb;
+    std::lock_guard<std::mutex> lock(g_align_mutex);
+    AlignState& S = g_align;
+    if (!S.stream || S.w == 0) return (int)cudaErrorNotReady;
+    if (stride < 1) return (int)cudaErrorInvalidValue;
+    cudaStream_t s = S.stream;
+    if (h_params_ref) memcpy(S.params_ref, h_params_ref, sizeof(S.params_ref));
+    if (h_params_tar) memcpy(S.params_tar, h_params_tar, sizeof(S.params_tar));
+    AlignParams P;
+    memcpy(P.ref, S.params_ref, sizeof(P.ref));
+    memcpy(P.tar, S.params_tar, sizeof(P.tar));
+    const int ow = VB_DIV_CEIL(S.w, stride), oh = VB_DIV_CEIL(S.h, stride);
+    const dim3 b(32, 4), g(VB_DIV_CEIL(ow, 32), VB_DIV_CEIL(oh, 4));
+    k_align_eval<<<g, b, 0, s>>>(make_view(S), P, ref_fid, tar_fid, S.photo ? 1 : 0, h_o_jacobian != nullptr,
+                                 apply_weights ? 1 : 0, stride);
+    VB_RETURN_IF_CUDA_ERROR();
+    const size_t n = (size_t)ow * oh;
+    if (h_o_residual) VB_CUDA(cudaMemcpyAsync(h_o_residual, S.residual, n * sizeof(float), cudaMemcpyDefault, s));
+    if (h_o_jacobian)
+        VB_CUDA(cudaMemcpyAsync(h_o_jacobian, S.jacobian, n * kAlignParams * sizeof(float), cudaMemcpyDefault, s));
     VB_CUDA(cudaStreamSynchronize(s));
     VB_RETURN_IF_CUDA_ERROR();
     return 0;
@@ -414,6 +450,13 @@ DLL_EXPORT int vb_align_frame_eval_gpu(int ref_fid, int tar_fid, const float* h_
                                        float* h_o_residual, float* h_o_jacobian, int apply_weights) {
     return align_frame_eval_gpu(ref_fid, tar_fid, h_params_ref, h_params_tar, h_o_residual, h_o_jacobian,
                                 apply_weights != 0);
+}
+
+DLL_EXPORT int vb_align_frame_eval_strided(int ref_fid, int tar_fid, const float* h_params_ref,
+                                           const float* h_params_tar, float* h_o_residual, float* h_o_jacobian,
+                                           int apply_weights, int stride) {
+    return align_frame_eval_strided(ref_fid, tar_fid, h_params_ref, h_params_tar, h_o_residual, h_o_jacobian,
+                                    apply_weights != 0, stride);
 }
 
 // reference gblur_gpu(GMatf src, GMatf& dst, sigma, ksize) (gblur.cu:47-72) on host/device buffers [depth][h][w]
