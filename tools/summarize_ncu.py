@@ -1,5 +1,6 @@
 """Condense one `ncu --set full` report into the handful of numbers the design discussion uses.
-usage: python tools/summarize_ncu.py gpurun_out/search_r01.ncu-rep profiles/r01_ncu_search  (writes .md and .json)"""
+usage: python tools/summarize_ncu.py gpurun_out/search_r01.ncu-rep profiles/r01_ncu_search  (writes .md and .json)
+       the first argument may also be the `ncu -i x.ncu-rep --page raw --csv` export of a report"""
 import csv
 import io
 import json
@@ -31,7 +32,10 @@ UNIT_SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
