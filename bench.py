@@ -416,6 +416,7 @@ def bench_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = voldor_b200.load_library()
+    voldor_b200.set_device(local_rank)  # the worker threads below inherit the library's device, not torch's
     lib.vb_profile_enable.argtypes = [C.c_int]
     lib.vb_profile_get.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     M = max(1, min(args.inflight, lib.vb_context_max()))

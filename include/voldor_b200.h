@@ -108,8 +108,12 @@ int vb_context_max(void);
 int vb_context_srand(unsigned int seed);  /* srand() of the current context's start-sample stream */
 int vb_context_rand(void);                /* one draw from it (test hook: consumption checks) */
 
-/* Select the CUDA device used by this process' state (default: current device). */
+/* Select the CUDA device of this process' state.  CUDA's current device is per host thread (default 0), so every entry
+ * point of the library makes this device current first: worker threads need no cudaSetDevice of their own.  Default:
+ * the device that was current in the thread that made the first call into the library. */
 int vb_set_device(int device);
+/* Test hook: the CUDA device an entry point would run on when called from this host thread. */
+int vb_debug_thread_device(void);
 
 /* In-library CUDA-event timing of the dominant kernel (fused cost + random depth search), for roofline
  * reporting.  Enabling it adds one event synchronisation per launch, so it is off by default. */

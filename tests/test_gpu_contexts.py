@@ -103,3 +103,21 @@ def test_context_zero_unaffected_by_other_contexts():
     ref = oracle_host.run_window(oracle_host.fresh_reference_copy("solo"), *args, config=CFG, boot=boot)
     for key in ("poses", "poses_covar", "depth", "depth_conf"):
         assert ffi.bits_equal(a[key], ref[key]), key
+
+
+def test_library_device_follows_vb_set_device_in_every_host_thread():
+    """CUDA's current device is per thread and defaults to 0: a worker thread must still run on the library's device"""
+    import torch
+
+    lib = voldor_b200.load_library()
+    n = torch.cuda.device_count()
+    target = n - 1
+    voldor_b200.set_device(target)
+    try:
+        seen = []
+        t = threading.Thread(target=lambda: seen.append(lib.vb_debug_thread_device()))
+        t.start()
+        t.join()
+        assert seen == [target]
+    finally:
+        voldor_b200.set_device(0)

@@ -4,6 +4,6 @@ The compute lives in voldor_b200/libvoldor_b200.so (hand-written CUDA, built in-
 `__graft_entry__.build()`).  There is no CPU fallback: importing the bindings without the library, or
 calling them without a CUDA device, raises."""
 from .pyvoldor_vo import (voldor, load_library, set_bootstrap_override, voldor_ex, select_context,  # noqa: F401
-                          context_srand)
+                          context_srand, set_device)
 
-__all__ = ["voldor", "voldor_ex", "load_library", "set_bootstrap_override", "select_context", "context_srand"]
+__all__ = ["voldor", "voldor_ex", "load_library", "set_bootstrap_override", "select_context", "context_srand", "set_device"]

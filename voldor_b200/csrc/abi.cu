@@ -11,7 +11,8 @@
 
 // Every entry point works on the calling host thread's execution context (context.h; context 0 unless the thread
 // selected another one) and holds that context's mutex for the duration of the call.
-#define VB_ENTER_CONTEXT()                \
+#define VB_ENTER_CONTEXT()                    \
+    vb::enter_device();                       \
     vb::Context& cx = vb::current_context(); \
     std::lock_guard<std::recursive_mutex> lock(cx.mutex)
 
@@ -230,7 +231,7 @@ DLL_EXPORT int vb_optimize_depth_gpu(float** h_flows, float** h_rigidnesses, flo
                               no_change_prob, range_factor, update_rigidness_only != 0);
 }
 
-DLL_EXPORT int vb_set_device(int device) { return (int)cudaSetDevice(device); }
+DLL_EXPORT int vb_set_device(int device) { return vb::set_library_device(device); }
 DLL_EXPORT void vb_profile_enable(int on) {
     vb::KernelProfile& p = vb::current_context().prof;
     p.enabled = on != 0;

@@ -15,6 +15,7 @@
 #include "../../include/gpu_kernels.h"
 #include "../../include/voldor_b200.h"
 #include "common.cuh"
+#include "context.h"
 #include <cfloat>
 #include <cmath>
 #include <mutex>
@@ -346,6 +347,7 @@ AlignView make_view(AlignState& S) {
 int align_frame_init_gpu(float* h_images[], float* h_depths[], float* h_weights[], float* h_K, float vbf, float crw,
                          int N, int w, int h) {
     using namespace vb;
+    enter_device();
     std::lock_guard<std::mutex> lock(g_align_mutex);
     AlignState& S = g_align;
     if (!S.stream) VB_CUDA(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
@@ -386,6 +388,7 @@ int align_frame_init_gpu(float* h_images[], float* h_depths[], float* h_weights[
 int align_frame_eval_gpu(int ref_fid, int tar_fid, const float* h_params_ref, const float* h_params_tar,
                          float* h_o_residual, float* h_o_jacobian, const bool apply_weights) {
     using namespace vb;
+    enter_device();
     std::lock_guard<std::mutex> lock(g_align_mutex);
     AlignState& S = g_align;
     if (!S.stream || S.w == 0) return (int)cudaErrorNotReady;
@@ -416,6 +419,7 @@ int align_frame_eval_gpu(int ref_fid, int tar_fid, const float* h_params_ref, co
 static int align_frame_eval_strided(int ref_fid, int tar_fid, const float* h_params_ref, const float* h_params_tar,
                                     float* h_o_residual, float* h_o_jacobian, bool apply_weights, int stride) {
     using namespace vb;
+    enter_device();
     std::lock_guard<std::mutex> lock(g_align_mutex);
     AlignState& S = g_align;
     if (!S.stream || S.w == 0) return (int)cudaErrorNotReady;
@@ -461,6 +465,7 @@ DLL_EXPORT int vb_align_frame_eval_strided(int ref_fid, int tar_fid, const float
 
 // reference gblur_gpu(GMatf src, GMatf& dst, sigma, ksize) (gblur.cu:47-72) on host/device buffers [depth][h][w]
 DLL_EXPORT int vb_gblur_gpu(const float* h_src, float* h_dst, int w, int h, int depth, float sigma, int ksize) {
+    vb::enter_device();
     static std::mutex m;
     std::lock_guard<std::mutex> lock(m);
     // grow-only scratch: two image stacks + the half kernel (the reference allocates and frees a GMat per call)

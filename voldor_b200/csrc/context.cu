@@ -1,15 +1,35 @@
 // Registry of execution contexts (context.h) and their C entry points (include/voldor_b200.h).
 #include "context.h"
+#include <atomic>
 #include "../../include/py_export.h"
 #include "../../include/voldor_b200.h"
 
 namespace vb {
 
 namespace {
+std::atomic<int> g_device{-1};
 std::mutex g_registry_mutex;
 Context* g_contexts[kMaxContexts] = {nullptr};
 thread_local int t_selected = 0;
 }  // namespace
+
+void enter_device() {
+    int dev = g_device.load(std::memory_order_acquire);
+    if (dev < 0) {
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) return;  // no device: the CUDA calls that follow report it
+        int expected = -1;
+        g_device.compare_exchange_strong(expected, cur);
+        dev = g_device.load();
+    }
+    cudaSetDevice(dev);
+}
+
+int set_library_device(int device) {
+    const cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) g_device.store(device, std::memory_order_release);
+    return (int)e;
+}
 
 Context* context_at(int id) {
     if (id < 0 || id >= kMaxContexts) return nullptr;
@@ -39,6 +59,11 @@ VB_EXPORT int vb_context_srand(unsigned int seed) {
     std::lock_guard<std::recursive_mutex> lock(cx.mutex);
     cx.rnd->seed(seed);
     return 0;
+}
+VB_EXPORT int vb_debug_thread_device(void) {
+    vb::enter_device();
+    int dev = -1;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
 }
 VB_EXPORT int vb_context_rand(void) {
     vb::Context& cx = vb::current_context();

@@ -93,6 +93,13 @@ struct Context {
     }
 };
 
+// The CUDA device of this process' state.  CUDA's current device is a PER-THREAD setting that defaults to device 0, so
+// a worker thread created after the main thread chose a device would silently land on GPU 0: every entry point makes
+// the library's device current first (enter_device).  It is the device passed to vb_set_device(), else the device that
+// was current in the thread that made the first call into the library.
+void enter_device();
+int set_library_device(int device);
+
 // context `id` (created on first use); nullptr when id is out of range
 Context* context_at(int id);
 // the context the calling host thread selected (default 0)

@@ -617,6 +617,7 @@ int run_window(const float* flows_pt, const float* disparity_pt, const float* di
                float fx, float fy, float cx, float cy, float basefocal, int N, int N_dp, int w, int h,
                const char* config_pt, int* n_registered, float* poses_pt, float* poses_covar_pt, float* depth_pt,
                float* depth_conf_pt, int* iters_run, float* stats) {
+    enter_device();
     Context& context = current_context();
     std::lock_guard<std::recursive_mutex> lock(context.mutex);
     auto t0 = std::chrono::high_resolution_clock::now();

@@ -39,6 +39,13 @@ def load_library():
     return lib
 
 
+def set_device(device):
+    """CUDA device of this process' library state; applies to every host thread that calls into the library"""
+    rc = load_library().vb_set_device(int(device))
+    if rc != 0:
+        raise RuntimeError(f"vb_set_device({device}) failed with CUDA error {rc}")
+
+
 def select_context(ctx):
     """Bind the calling Python thread to execution context `ctx` (0 .. vb_context_max()-1); returns the previous one.
     Contexts are independent copies of the library's device state: windows issued from different threads on
