@@ -83,6 +83,12 @@ profile)
 gpus2)
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 4 --warmup 3 --no-extras --no-cpu-baseline > $out/bench_gpus2.json 2> $out/bench_gpus2.err
   tail -c 1500 $out/bench_gpus2.json; tail -3 $out/bench_gpus2.err ;;
+prune)
+  for v in on off; do
+    if [ $v = off ]; then export VB_NO_SEARCH_PRUNING=1; else unset VB_NO_SEARCH_PRUNING; fi
+    python bench.py --steps 6 --warmup 3 --no-extras --no-cpu-baseline > $out/bench_prune_$v.json 2> $out/bench_prune_$v.err
+    python -c "import json;l=json.loads(open('$out/bench_prune_$v.json').read().strip().splitlines()[-1]);print('pruning $v: value',round(l['value'],1),'e2e',round(l['e2e']['value'],1),'single',round(l['latency']['single_window']['value'],1),'search ms',round(l['roofline']['avg_launch_ms'],4),'parity',l['parity_checked'])" || tail -5 $out/bench_prune_$v.err
+  done; unset VB_NO_SEARCH_PRUNING ;;
 probe)
   tools/_build/tex_probe 27 > $out/tex_probe.json 2>&1; cat $out/tex_probe.json ;;
 launches)

