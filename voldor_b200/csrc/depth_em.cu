@@ -116,6 +116,8 @@ __device__ float pixel_cost(const DepthView& A, const CamBlock& C, const PriorCa
 __device__ __forceinline__ void try_candidate(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC, int x,
                                               int y, float cand) {
     const size_t idx = (size_t)y * A.pitch + x;
+    // a candidate equal to the pixel's own depth reproduces cost[idx] exactly and the strict '<' rejects it
+    if (__float_as_uint(A.depth[idx]) == __float_as_uint(cand)) return;
     const float c = pixel_cost(A, C, PC, x, y, cand);
     if (c < A.cost[idx]) {  // strict '<' (reference: optimize_depth.cu:201-207)
         A.depth[idx] = cand;
@@ -545,7 +547,19 @@ __global__ void __launch_bounds__(128)
     // the candidate for position p is the (possibly just updated) depth of position p - step
     int sx = rowdir ? first - step : o, sy = rowdir ? o : first - step;
     float cand = A.depth[(size_t)sy * A.pitch + sx];
-    for (int i = 0, pos = first; i < count; i++, pos += step) {
+    int i = 0, pos = first;
+    while (true) {
+        // A position that already holds the candidate's depth (bit for bit) cannot accept it: the candidate's cost is
+        // the very number stored in cost[] (same function of the same depth, weights and poses within this depth
+        // step), the comparison is strict, and the candidate handed on is unchanged.  About 44 % of the propagation
+        // candidates are such copies, so they are stepped over without evaluating the likelihood terms.  The chains
+        // of a warp run through this loop independently and meet again for the next evaluation.
+        while (i < count) {
+            const int x = rowdir ? pos : o, y = rowdir ? o : pos;
+            if (__float_as_uint(A.depth[(size_t)y * A.pitch + x]) != __float_as_uint(cand)) break;
+            i++, pos += step;
+        }
+        if (i >= count) break;
         const int x = rowdir ? pos : o, y = rowdir ? o : pos;
         const size_t idx = (size_t)y * A.pitch + x;
         const float c = pixel_cost_group<G, TPL>(A, C, PC, x, y, cand, gl, gmask, gbase);
@@ -556,6 +570,7 @@ __global__ void __launch_bounds__(128)
         } else {
             cand = A.depth[idx];
         }
+        i++, pos += step;
     }
 }
 
