@@ -42,7 +42,7 @@ p3ptime)
     python tools/summarize_launches.py $out/p3p_$v.csv | tail -4
   done; unset VB_P3P_LEGACY ;;
 inflight)
-  for m in 4 6 8; do
+  for m in ${INFLIGHT_LIST:-4 6 8}; do
     python bench.py --steps 6 --warmup 3 --inflight $m --no-extras --no-cpu-baseline --no-parity > $out/bench_inflight$m.json 2> $out/bench_inflight$m.err
     python - <<PY
 import json
