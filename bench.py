@@ -391,7 +391,7 @@ def search_kernel_roofline(lib, runner, ncu_json=None):
             traffic, issue_pct = cap.get("dram_bytes_per_launch"), cap.get("issue_active_pct")
         except (OSError, ValueError):
             pass
-    return {"bound": "hbm", "kernel": "k_cost_and_random_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    return {"bound": "hbm", "kernel": "k_cost_and_random_search_pruned", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "launches_timed": sl.value,
             "binding_bound": "instruction issue", "issue_slots_busy_pct_ncu": issue_pct}
@@ -527,9 +527,10 @@ def bench_ours(args, rank, world, local_rank):
 
         roof = search_kernel_roofline(lib, r0, "r02_ncu_search_kernel.json")
         roof["whole_iteration"] = whole_iteration_roofline(CASES["C2"], iters_res / world, ms_res)
-        roof["note"] = ("instruction-issue-bound kernel (6 powf + expf + logf + ~10 IEEE divisions per likelihood term, "
-                        "all pinned by bit-parity): HBM fraction reported as BASELINE.json asks; the window state is L2 "
-                        "resident; see DESIGN.md §6 and profiles/")
+        roof["note"] = ("instruction-issue-bound kernel (Fisk posteriors: 6 powers + expf + logf + 7 IEEE divisions per "
+                        "likelihood term, rounding points pinned by bit-parity; candidates that provably cannot win are "
+                        "rejected after their first terms): HBM fraction reported as BASELINE.json asks; see DESIGN.md "
+                        "§6 and profiles/r02_summary.md for the issue roofline of the whole path")
         # kernel launches per window (counted once, outside the timed region, with the CUPTI-based profiler)
         try:
             from torch.profiler import ProfilerActivity, profile
