@@ -377,6 +377,8 @@ def search_kernel_roofline(lib, runner, ncu_json=None):
     runner.run("resident")
     sm, sl = C.c_double(0), C.c_longlong(0)
     lib.vb_profile_get(C.byref(sm), C.byref(sl))
+    ms3, n3 = (C.c_double * 3)(), (C.c_longlong * 3)()
+    lib.vb_profile_get_more(ms3, n3)
     lib.vb_profile_enable(0)
     N, N_dp, w, h = runner.N, runner.N_dp, runner.w, runner.h
     alg_bytes = w * h * (12 * N + 60 + 12 * N_dp)  # + prior depth / pconf / conf fetches
@@ -391,10 +393,23 @@ def search_kernel_roofline(lib, runner, ncu_json=None):
             traffic, issue_pct = cap.get("dram_bytes_per_launch"), cap.get("issue_active_pct")
         except (OSError, ValueError):
             pass
+    def other(k, name, nbytes, what):
+        if n3[k] == 0:
+            return None
+        t = ms3[k] / n3[k]
+        return {"kernel": name, "what": what, "algorithmic_bytes": nbytes, "avg_ms": t, "runs_timed": n3[k],
+                "achieved": nbytes / (t * 1e-3) / 1e9, "unit": "GB/s", "frac": nbytes / (t * 1e-3) / 1e9 / peak}
+
+    px = w * h
+    others = [other(0, "k_update_rigidness", px * (12 * N + 4 + 16 * N_dp), "E-step: flows 8N + rigidness out 4N + depth 4 per pixel"),
+              other(1, "k_fb_rows + k_fb_posterior + k_fb_cols + k_fb_posterior", px * 48 * N,
+                    "one forward-backward smoothing of the N rigidness maps: 12 map-sized reads/writes"),
+              other(2, "k_local_propagation_group x4", 4 * px * (12 * N + 12 + 12 * N_dp), "the four local-propagation passes of one depth step")]
     return {"bound": "hbm", "kernel": "k_cost_and_random_search_pruned", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "launches_timed": sl.value,
-            "binding_bound": "instruction issue", "issue_slots_busy_pct_ncu": issue_pct}
+            "binding_bound": "instruction issue", "issue_slots_busy_pct_ncu": issue_pct,
+            "other_kernels": [o for o in others if o]}
 
 
 def whole_iteration_roofline(case, iters, ms):
@@ -419,6 +434,7 @@ def bench_ours(args, rank, world, local_rank):
     voldor_b200.set_device(local_rank)  # the worker threads below inherit the library's device, not torch's
     lib.vb_profile_enable.argtypes = [C.c_int]
     lib.vb_profile_get.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    lib.vb_profile_get_more.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     M = max(1, min(args.inflight, lib.vb_context_max()))
 
     # context k of rank r solves its own window (different scene seeds); context 0 = the window of round 1's bench

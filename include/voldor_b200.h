@@ -119,6 +119,9 @@ int vb_debug_thread_device(void);
  * reporting.  Enabling it adds one event synchronisation per launch, so it is off by default. */
 void vb_profile_enable(int on);
 void vb_profile_get(double* search_ms, long long* search_launches);
+/* also timed while profiling is on: ms3 / counts3 = { E-step kernel, one forward-backward smoothing of the rigidness
+ * maps (4 launches), the four local-propagation passes of one depth step } */
+void vb_profile_get_more(double* ms3, long long* counts3);
 /* Counters of the on-device fixed-point loops since the last vb_profile_enable():
  * out5 = { mean-shift runs, their iterations, start-sample trials, robust-fit runs, their iterations }. */
 void vb_profile_counters(long long* out5);

@@ -236,6 +236,7 @@ DLL_EXPORT void vb_profile_enable(int on) {
     vb::KernelProfile& p = vb::current_context().prof;
     p.enabled = on != 0;
     p.search_ms = 0, p.search_launches = 0;
+    p.estep_ms = p.smooth_ms = p.local_ms = 0, p.estep_launches = p.smooth_runs = p.local_runs = 0;
     p.meanshift_runs = p.meanshift_iters = p.meanshift_trials = p.robust_runs = p.robust_iters = 0;
 }
 DLL_EXPORT void vb_profile_counters(long long* out5) {
@@ -247,6 +248,11 @@ DLL_EXPORT void vb_profile_get(double* search_ms, long long* search_launches) {
     vb::KernelProfile& p = vb::current_context().prof;
     if (search_ms) *search_ms = p.search_ms;
     if (search_launches) *search_launches = p.search_launches;
+}
+DLL_EXPORT void vb_profile_get_more(double* ms3, long long* counts3) {
+    vb::KernelProfile& p = vb::current_context().prof;
+    ms3[0] = p.estep_ms, ms3[1] = p.smooth_ms, ms3[2] = p.local_ms;
+    counts3[0] = p.estep_launches, counts3[1] = p.smooth_runs, counts3[2] = p.local_runs;
 }
 DLL_EXPORT int vb_debug_pose_mode_phases(long long* out24) {
     vb::PoseMode& M = vb::current_context().M;

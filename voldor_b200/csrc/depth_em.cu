@@ -1000,15 +1000,38 @@ int DepthEM::run(int N, int N_dp, const DepthHyper& hp, bool update_rigidness_on
             launch_global<DIR_T2B>(A, cam, pcam, hp.global_prop_step, s);
         }
         if (hp.local_prop_width > 0) {
+            if (prof.enabled) cudaEventRecord(prof.ev0, s);
             launch_local<DIR_L2R>(A, cam, pcam, hp.local_prop_width, s);
             launch_local<DIR_B2T>(A, cam, pcam, hp.local_prop_width, s);
             launch_local<DIR_R2L>(A, cam, pcam, hp.local_prop_width, s);
             launch_local<DIR_T2B>(A, cam, pcam, hp.local_prop_width, s);
+            if (prof.enabled) {
+                cudaEventRecord(prof.ev1, s);
+                cudaEventSynchronize(prof.ev1);
+                float ms = 0;
+                cudaEventElapsedTime(&ms, prof.ev0, prof.ev1);
+                prof.local_ms += ms, prof.local_runs++;
+            }
         }
         VB_RETURN_IF_CUDA_ERROR();
     }
     A.rig = rig.ptr;  // the E-step writes the raw posteriors
-    k_update_rigidness<<<pg, pb, 0, s>>>(A, cam, pcam);
+    {
+        KernelProfile none;
+        KernelProfile& prof = this->prof ? *this->prof : none;
+        if (prof.enabled) {
+            if (!prof.ev0) cudaEventCreate(&prof.ev0), cudaEventCreate(&prof.ev1);
+            cudaEventRecord(prof.ev0, s);
+        }
+        k_update_rigidness<<<pg, pb, 0, s>>>(A, cam, pcam);
+        if (prof.enabled) {
+            cudaEventRecord(prof.ev1, s);
+            cudaEventSynchronize(prof.ev1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, prof.ev0, prof.ev1);
+            prof.estep_ms += ms, prof.estep_launches++;
+        }
+    }
     VB_RETURN_IF_CUDA_ERROR();
     if (overlap_smoothing && hp.fb_smooth && N > 0) {
         // smooth the new rigidness maps for the next M-step on the side stream, concurrently with whatever the
@@ -1019,7 +1042,19 @@ int DepthEM::run(int N, int N_dp, const DepthHyper& hp, bool update_rigidness_on
         StackView S{rig_s.ptr, rig_s.pitch, rig_s.layer_elems()};
         StackView F{fb_fwd.ptr, fb_fwd.pitch, fb_fwd.layer_elems()};
         StackView B{fb_bwd.ptr, fb_bwd.pitch, fb_bwd.layer_elems()};
-        fb_smooth_stack(E, S, F, B, N, w, h, hp.s0_ems_prob, hp.no_change_prob, side);
+        {
+            KernelProfile none;
+            KernelProfile& prof = this->prof ? *this->prof : none;
+            if (prof.enabled) cudaEventRecord(prof.ev0, side);
+            fb_smooth_stack(E, S, F, B, N, w, h, hp.s0_ems_prob, hp.no_change_prob, side);
+            if (prof.enabled) {
+                cudaEventRecord(prof.ev1, side);
+                cudaEventSynchronize(prof.ev1);
+                float ms = 0;
+                cudaEventElapsedTime(&ms, prof.ev0, prof.ev1);
+                prof.smooth_ms += ms, prof.smooth_runs++;
+            }
+        }
         VB_CUDA(cudaEventRecord(ev_smooth_done, side));
         smooth_layers = N, smooth_s0 = hp.s0_ems_prob, smooth_nc = hp.no_change_prob;
         VB_RETURN_IF_CUDA_ERROR();

@@ -78,6 +78,12 @@ struct KernelProfile {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double search_ms = 0;      // accumulated duration of k_cost_and_random_search
     long long search_launches = 0;
+    double estep_ms = 0;       // k_update_rigidness
+    long long estep_launches = 0;
+    double smooth_ms = 0;      // one forward-backward smoothing of the N rigidness maps (rows, posterior, cols, posterior)
+    long long smooth_runs = 0;
+    double local_ms = 0;       // the four local-propagation passes of one depth step
+    long long local_runs = 0;
     long long launches = 0;    // all kernel launches issued by the depth step / pose stages since reset
     // fixed-point loops of the pose-mode kernels (always counted; host-side bookkeeping only)
     long long meanshift_runs = 0, meanshift_iters = 0, meanshift_trials = 0;
