@@ -141,6 +141,10 @@ int vb_debug_rvec_to_matrix(const float* rvecs, int n, float* R_device, float* R
  * be exactly `keep` draws past where it was.  Returns 0, or 1 if the state array could not be captured. */
 int vb_debug_rand_speculate(int draw, int keep);
 
+/* Test hook: parse a flag string with this library's flag grammar (csrc/config.h; reference voldor/config.h:110-253,
+ * py_export.cpp:15-25) and dump all 56 fields as doubles; returns the number of fields written. */
+int vb_debug_config_dump(const char* flags, float fx, float fy, float cx, float cy, float basefocal, double* out);
+
 /* Library self-description: returns a static string "voldor_b200 <version> sm_100a". */
 const char* vb_version(void);
 

@@ -687,6 +687,31 @@ VB_EXPORT int vb_py_voldor_wrapper_ex(const float* flows, const float* disparity
                           iters_run, stats);
 }
 
+// Test hook: the flag parser of this library (csrc/config.h) on a flag string, every field dumped in the order of
+// oracle/ref_shim/ref_config_probe.cpp (which dumps the reference's own Config for the same string).
+VB_EXPORT int vb_debug_config_dump(const char* flags, float fx, float fy, float cx, float cy, float basefocal,
+                                   double* out) {
+    vb::Config cfg;
+    cfg.fx = fx, cfg.cx = cx, cfg.fy = fy, cfg.cy = cy, cfg.basefocal = basefocal;
+    cfg.read(flags);
+    int k = 0;
+#define F(name) out[k++] = (double)cfg.name
+    F(omega); F(disp_delta); F(delta); F(basefocal);
+    F(rg_refine); F(rg_refine_last_only); F(rg_trunc_sigma); F(rg_covar_reg_lambda); F(rg_pose_scaling); F(rg_max_iters); F(rg_epsilon);
+    F(resize_factor); F(abs_resize_factor); F(fx); F(fy); F(cx); F(cy); F(exclusive_gpu_context);
+    F(debug); F(silent); F(save_everything); F(viz_img_per_row); F(viz_depth_scale);
+    F(lambda); F(meanshift_kernel_var); F(meanshift_rvec_scale); F(norm_world_scale);
+    F(cpu_p3p); F(lambdatwist); F(n_poses_to_sample); F(pose_sample_min_depth); F(pose_sample_max_depth); F(max_trace_on_flow);
+    F(rigidness_threshold); F(rigidness_sum_threshold);
+    F(trunc_rigidness_density); F(trunc_sample_density); F(no_trunc_iters); F(max_iters); F(min_iters_after_trunc);
+    F(fb_smooth); F(fb_emm); F(fb_no_change_prob);
+    F(optimize_depth); F(depth_rand_samples); F(depth_global_prop_step); F(depth_local_prop_width); F(depth_range_factor);
+    F(meanshift_max_iters); F(meanshift_max_init_trials); F(meanshift_good_init_confidence); F(meanshift_epsilon);
+    F(kitti_estimate_ground); F(kitti_ground_holo_width); F(kitti_ground_roi); F(kitti_ground_meanshift_kernel_var);
+#undef F
+    return k;
+}
+
 VB_EXPORT int vb_bootstrap_from_flow(const float* flow, int w, int h, const float* K9, float* R9, float* t3, float* depth) {
     return vb::boot::bootstrap_from_flow(flow, w, h, K9, R9, t3, depth) ? 0 : 1;
 }
