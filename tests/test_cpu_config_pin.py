@@ -1,5 +1,5 @@
 """The flag grammar and every default of this library's Config (csrc/config.h) against the reference's OWN struct Config:
-voldor/config.h compiled unmodified (oracle/ref_shim/ref_config_probe.cpp behind a declaration-only OpenCV stand-in)
+voldor/config.h compiled unmodified (oracle/ref_shim/ref_config_probe.cpp against the OpenCV stand-in oracle/ref_shim/cv_min)
 and driven exactly like voldor/py_export.cpp:15-25 drives it.  Covers the defaults, every flag one at a time, the
 str_to_arg fall-through (fractional values given to integer fields), the value-less switches and realistic strings."""
 import ctypes as C
