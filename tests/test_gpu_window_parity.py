@@ -172,6 +172,24 @@ def test_c2_benchmarked_configuration_30_iterations_bit_exact():
     _compare("window C2 640x480x8 30 iterations (bench.py workload) resident-vs-ref", mine, ref)
 
 
+@pytest.mark.parametrize("name", ["C3", "C5"])
+def test_benchmarked_extra_configurations_full_iterations_bit_exact(name):
+    """the `extra` lines of bench.py (BASELINE.json configs[2] and configs[4]) exactly as timed: full image size,
+    window length, hypothesis count AND iteration count (C5: 1280x960, 12 flows, 50 EM iterations, depth prior)"""
+    import bench
+
+    win, kw, boot, cfg = bench.make_case(name)
+    assert boot is None
+    args = (win["flows"], win["fx"], win["fy"], win["cx"], win["cy"])
+    ffi.libc_srand(2000)
+    ref = oracle_host.run_window("ref", *args, config=cfg, **kw)
+    ffi.libc_srand(2000)
+    mine = voldor_b200.voldor_ex(*args, config=cfg, **kw)
+    c = bench.CASES[name]
+    assert ref["n_registered"] == c["N"] and ref["iters"] == c["iters"]
+    _compare(f"window {name} {c['w']}x{c['h']}x{c['N']} {c['iters']} iterations (bench.py extra) resident-vs-ref", mine, ref)
+
+
 def test_c1_configuration_bit_exact():
     """BASELINE.json configs[0]: single 320x240 frame, 4 flows, 10 EM iterations, monocular"""
     w, h, N, iters = 320, 240, 4, 10

@@ -53,6 +53,19 @@ except Exception as e:
     print("inflight $m failed", e, open("$out/bench_inflight$m.err").read()[-1500:])
 PY
   done ;;
+conns)
+  # hardware work queues: 6+ contexts x 2 streams may alias onto the default 8 connections
+  for c in 8 32; do for m in 6 8; do
+    CUDA_DEVICE_MAX_CONNECTIONS=$c python bench.py --steps 6 --warmup 3 --inflight $m --no-extras --no-cpu-baseline --no-parity > $out/bench_conn${c}_m$m.json 2> $out/bench_conn${c}_m$m.err
+    python - <<PY
+import json
+try:
+    l=json.loads(open("$out/bench_conn${c}_m$m.json").read().strip().splitlines()[-1])
+    print("connections $c inflight $m value", round(l["value"],1), "e2e", round(l["e2e"]["value"],1))
+except Exception as e:
+    print("connections $c inflight $m failed", e, open("$out/bench_conn${c}_m$m.err").read()[-800:])
+PY
+  done; done ;;
 weights)
   tools/_build/tex_probe weights $out/tex_weights.bin > $out/tex_weights.json 2>&1; cat $out/tex_weights.json ;;
 tpl)
