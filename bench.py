@@ -48,6 +48,8 @@ import time
 
 import numpy as np
 
+# hardware work queues for the windows in flight (voldor_b200/csrc/context.cu); must be set before CUDA is initialised
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))

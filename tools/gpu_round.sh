@@ -54,18 +54,18 @@ except Exception as e:
 PY
   done ;;
 conns)
-  # hardware work queues: 6+ contexts x 2 streams may alias onto the default 8 connections
-  for c in 8 32; do for m in 6 8; do
-    CUDA_DEVICE_MAX_CONNECTIONS=$c python bench.py --steps 6 --warmup 3 --inflight $m --no-extras --no-cpu-baseline --no-parity > $out/bench_conn${c}_m$m.json 2> $out/bench_conn${c}_m$m.err
+  # hardware work queues: 6+ contexts x 2 streams alias onto the default 8 connections; A/B on one box, two rounds
+  for rep in 1 2; do for c in 8 32; do for m in ${INFLIGHT_LIST:-6 8 12}; do
+    CUDA_DEVICE_MAX_CONNECTIONS=$c python bench.py --steps 6 --warmup 3 --inflight $m --no-extras --no-cpu-baseline --no-parity > $out/bench_conn${c}_m${m}_$rep.json 2> $out/bench_conn${c}_m${m}_$rep.err
     python - <<PY
 import json
 try:
-    l=json.loads(open("$out/bench_conn${c}_m$m.json").read().strip().splitlines()[-1])
-    print("connections $c inflight $m value", round(l["value"],1), "e2e", round(l["e2e"]["value"],1))
+    l=json.loads(open("$out/bench_conn${c}_m${m}_$rep.json").read().strip().splitlines()[-1])
+    print("round $rep connections $c inflight $m value", round(l["value"],1), "e2e", round(l["e2e"]["value"],1))
 except Exception as e:
-    print("connections $c inflight $m failed", e, open("$out/bench_conn${c}_m$m.err").read()[-800:])
+    print("connections $c inflight $m failed", e, open("$out/bench_conn${c}_m${m}_$rep.err").read()[-800:])
 PY
-  done; done ;;
+  done; done; done ;;
 weights)
   tools/_build/tex_probe weights $out/tex_weights.bin > $out/tex_weights.json 2>&1; cat $out/tex_weights.json ;;
 tpl)
