@@ -93,6 +93,12 @@ profile)
   # (3) launch list of the bench command itself
   ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file $out/launches_bench.csv python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline --no-parity > $out/bench_under_ncu.log 2>&1
   echo "bench launches rc=$?"; wc -l $out/launches_bench.csv ;;
+localsrc)
+  # source-level view of one local-propagation launch in the middle of a window (iteration 16 of 20)
+  ncu --set full --clock-control none --import-source on -k regex:k_local_propagation_group -s 60 -c 1 -f -o $out/localsrc python tools/profile_window.py --iters 20 > $out/ncu_localsrc.log 2>&1
+  ncu -i $out/localsrc.ncu-rep --page source --csv > $out/localprop_source.csv 2>/dev/null
+  ncu -i $out/localsrc.ncu-rep --page raw --csv > $out/localsrc_raw.csv 2>/dev/null
+  rm -f $out/localsrc.ncu-rep; ls -la $out/localprop_source.csv ;;
 gpus2)
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 4 --warmup 3 --no-extras --no-cpu-baseline > $out/bench_gpus2.json 2> $out/bench_gpus2.err
   tail -c 1500 $out/bench_gpus2.json; tail -3 $out/bench_gpus2.err ;;
