@@ -464,15 +464,55 @@ __device__ __forceinline__ float pixel_cost_group(const DepthView& A, const CamB
     float my_w[TPL], my_log[TPL];
 #pragma unroll
     for (int j = 0; j < TPL; j++) my_valid[j] = false, my_w[j] = 0.f, my_log[j] = 0.f, m_px1[j] = m_py1[j] = m_px2[j] = m_py2[j] = 0.f;
-    for (int f = 0; f < A.N; f++) {
-        float px2, py2;
-        rigid_move(C.R[f], C.t[f], ox, oy, oz);
-        project(C, ox, oy, oz, px2, py2);
-        if (oz > 0 && px1 >= 0 && px1 < fw && py1 >= 0 && py1 < fh) {
+    if constexpr (TPL == 1) {
+        // One term per lane: every lane still walks the rigid moves (frame f's camera-space point is a running
+        // product), but only lane f projects frame f — the two IEEE divisions and the in-view tests of a frame are
+        // done once per group instead of once per lane.  Which frames take part and where each one fetches from
+        // (the position of the last earlier frame that took part, or the pixel itself) follows from two group-wide
+        // bit masks: Z_f = "point in front of camera f", P_f = "projection of frame f inside the image".
+        float mx = 0.f, my = 0.f, mz = 0.f;
+        for (int f = 0; f < A.N; f++) {
+            rigid_move(C.R[f], C.t[f], ox, oy, oz);
+            if (f == gl) mx = ox, my = oy, mz = oz;
+        }
+        float px2 = 0.f, py2 = 0.f;
+        bool in_front = false, inside = false;
+        if (gl < A.N) {
+            project(C, mx, my, mz, px2, py2);
+            in_front = mz > 0;
+            inside = px2 >= 0 && px2 < fw && py2 >= 0 && py2 < fh;
+        }
+        const unsigned zb = __ballot_sync(gmask, in_front) >> gbase;
+        const unsigned pb = __ballot_sync(gmask, inside) >> gbase;
+        const unsigned all = (A.N >= 32) ? 0xffffffffu : ((1u << A.N) - 1u);
+        int src = gl - 1;  // frame whose projected position this lane's frame fetches at; -1 = the pixel itself
+        bool valid = gl < A.N;
+        if ((zb & pb & all) != all) {
+            // some frame drops out: replay the reference's sequential rule (stale px1) on the masks
+            bool at_inside = true;  // the pixel itself lies inside the image
+            int last = -1;
+            valid = false;
+            for (int f = 0; f < A.N; f++) {
+                const bool v = ((zb >> f) & 1u) && at_inside;
+                if (f == gl) valid = v, src = last;
+                if (v) last = f, at_inside = (pb >> f) & 1u;
+            }
+        }
+        const float sx = __shfl_sync(gmask, px2, gbase + max(src, 0));
+        const float sy = __shfl_sync(gmask, py2, gbase + max(src, 0));
+        m_px1[0] = src < 0 ? fpx : sx, m_py1[0] = src < 0 ? fpy : sy;
+        m_px2[0] = px2, m_py2[0] = py2, my_valid[0] = valid;
+    } else {
+        for (int f = 0; f < A.N; f++) {
+            float px2, py2;
+            rigid_move(C.R[f], C.t[f], ox, oy, oz);
+            project(C, ox, oy, oz, px2, py2);
+            if (oz > 0 && px1 >= 0 && px1 < fw && py1 >= 0 && py1 < fh) {
 #pragma unroll
-            for (int j = 0; j < TPL; j++)
-                if (f == gl + j * G) m_px1[j] = px1, m_py1[j] = py1, m_px2[j] = px2, m_py2[j] = py2, my_valid[j] = true;
-            px1 = px2, py1 = py2;
+                for (int j = 0; j < TPL; j++)
+                    if (f == gl + j * G) m_px1[j] = px1, m_py1[j] = py1, m_px2[j] = px2, m_py2[j] = py2, my_valid[j] = true;
+                px1 = px2, py1 = py2;
+            }
         }
     }
 #pragma unroll
@@ -506,11 +546,11 @@ __device__ __forceinline__ float pixel_cost_group(const DepthView& A, const CamB
     const int terms = A.N + A.N_dp;
 #pragma unroll
     for (int j = 0; j < TPL; j++) {
+        const unsigned taking_part = __ballot_sync(gmask, my_valid[j]) >> gbase;
         for (int k = j * G; k < terms && k < (j + 1) * G; k++) {
             const float w = __shfl_sync(gmask, my_w[j], gbase + k - j * G);
             const float lg = __shfl_sync(gmask, my_log[j], gbase + k - j * G);
-            const int v = __shfl_sync(gmask, (int)my_valid[j], gbase + k - j * G);
-            if (v) {
+            if ((taking_part >> (k - j * G)) & 1u) {
                 cost_sum = f_fma(-w, lg, cost_sum);
                 weight_sum = f_add(weight_sum, w);
             }
