@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(128)
 // position of frame f depends on the in-view tests of all earlier frames (stale px1 rule).
 // The result is returned on every lane of the group.
 // ------------------------------------------------------------------------------------------------
-template <int G, int TPL>
+template <int G, int TPL, bool SHARE>
 __device__ __forceinline__ float pixel_cost_group(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC,
                                                   int px, int py, float depth, int gl, unsigned gmask, int gbase) {
     // lane gl owns the terms k = gl, gl+G, ... (slot k/G); terms 0..N-1 are flows, N..N+N_dp-1 priors
@@ -464,7 +464,7 @@ __device__ __forceinline__ float pixel_cost_group(const DepthView& A, const CamB
     float my_w[TPL], my_log[TPL];
 #pragma unroll
     for (int j = 0; j < TPL; j++) my_valid[j] = false, my_w[j] = 0.f, my_log[j] = 0.f, m_px1[j] = m_py1[j] = m_px2[j] = m_py2[j] = 0.f;
-    if constexpr (TPL == 1) {
+    if constexpr (TPL == 1 && SHARE) {
         // One term per lane: every lane still walks the rigid moves (frame f's camera-space point is a running
         // product), but only lane f projects frame f — the two IEEE divisions and the in-view tests of a frame are
         // done once per group instead of once per lane.  Which frames take part and where each one fetches from
@@ -562,7 +562,7 @@ __device__ __forceinline__ float pixel_cost_group(const DepthView& A, const CamB
 
 // local propagation with G lanes per chain: block = 128 threads = 128/G chains.
 // chain index c -> (o, seg) with o fastest.
-template <int DIR, int G, int TPL>
+template <int DIR, int G, int TPL, bool SHARE>
 __global__ void __launch_bounds__(128)
     k_local_propagation_group(const DepthView A, const __grid_constant__ CamBlock C,
                               const __grid_constant__ PriorCamBlock PC, int width, int n_other, int n_seg) {
@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(128)
         if (i >= count) break;
         const int x = rowdir ? pos : o, y = rowdir ? o : pos;
         const size_t idx = (size_t)y * A.pitch + x;
-        const float c = pixel_cost_group<G, TPL>(A, C, PC, x, y, cand, gl, gmask, gbase);
+        const float c = pixel_cost_group<G, TPL, SHARE>(A, C, PC, x, y, cand, gl, gmask, gbase);
         const float cur_cost = A.cost[idx];
         if (c < cur_cost) {
             if (gl == 0) A.depth[idx] = cand, A.cost[idx] = c;
@@ -838,7 +838,24 @@ template <int DIR, int G, int TPL>
 void launch_local_group(const DepthView& A, const CamBlock& C, const PriorCamBlock& PC, int width, int other,
                         int nseg, cudaStream_t s) {
     const long long threads = (long long)other * nseg * G;
-    k_local_propagation_group<DIR, G, TPL><<<(unsigned)VB_DIV_CEIL(threads, 128), 128, 0, s>>>(A, C, PC, width, other, nseg);
+    const unsigned blocks = (unsigned)VB_DIV_CEIL(threads, 128);
+    // Sharing the projections of a candidate across the lanes of its group (pixel_cost_group) removes a fifth of the
+    // instructions but lengthens the dependent path of one evaluation (projection -> ballot -> shuffle -> fetch instead
+    // of projections overlapping the next rigid move).  Measured alone: 0.449 -> 0.401 ms at 16 warps per SM (640x480x8),
+    // 0.307 -> 0.375 ms at 2 warps per SM (320x240x4).  A launch that cannot fill the GPU anyway keeps every lane
+    // self-contained.  VB_LOCAL_SHARE=0/1 forces one variant (profiling).
+    static const int forced = [] { const char* e = getenv("VB_LOCAL_SHARE"); return e ? atoi(e) : -1; }();
+    static const int sms = [] {
+        int dev = 0, n = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n;
+    }();
+    const bool share = TPL == 1 && (forced >= 0 ? forced != 0 : threads / 32 >= 8LL * sms);
+    if (share)
+        k_local_propagation_group<DIR, G, TPL, TPL == 1><<<blocks, 128, 0, s>>>(A, C, PC, width, other, nseg);
+    else
+        k_local_propagation_group<DIR, G, TPL, false><<<blocks, 128, 0, s>>>(A, C, PC, width, other, nseg);
 }
 
 template <int DIR>
