@@ -102,6 +102,9 @@ localsrc)
 gpus2)
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 4 --warmup 3 --no-extras --no-cpu-baseline > $out/bench_gpus2.json 2> $out/bench_gpus2.err
   tail -c 1500 $out/bench_gpus2.json; tail -3 $out/bench_gpus2.err ;;
+gpus8)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --steps 4 --warmup 3 --no-extras --no-cpu-baseline > $out/bench_gpus8.json 2> $out/bench_gpus8.err
+  tail -c 1500 $out/bench_gpus8.json; tail -3 $out/bench_gpus8.err ;;
 prune)
   for v in on off; do
     if [ $v = off ]; then export VB_NO_SEARCH_PRUNING=1; else unset VB_NO_SEARCH_PRUNING; fi
