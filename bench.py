@@ -193,6 +193,7 @@ def bench_reference(args, rank, world):
         # restatement; the pose of its essential-matrix bootstrap is handed in (OpenCV is not in this image), the
         # closed-form depth of the bootstrap is computed by the reference inside the timed region
         own_host = os.path.exists(oracle_host.REF_HOST)
+        short_windows = []
         R0 = np.asarray(boot[0], np.float32).reshape(3, 3)
         epipolar = (R0, (R0.T.astype(np.float64) @ np.asarray(boot[1], np.float64)).astype(np.float32))
         for i in range(args.warmup + args.steps):
@@ -206,8 +207,11 @@ def bench_reference(args, rank, world):
                 # py_voldor_wrapper of the reference: its own host code, compiled unmodified (oracle/_ref)
                 r = oracle_host.run_reference_host(backend, win["flows"], win["fx"], win["fy"], win["cx"], win["cy"],
                                                    config=CONFIG, epipolar=epipolar)
-                r["iters"] = EM_ITERS  # truncation is off and every frame registers: checked below
-                assert r["n_registered"] == NFLOWS, r["n_registered"]
+                # py_voldor_wrapper does not report the iteration count; with truncation off the loop runs max_iters
+                # times as long as a camera is left (voldor.cpp:135).  A window that lost cameras is noted on the line.
+                r["iters"] = EM_ITERS if r["n_registered"] > 0 else 0
+                if r["n_registered"] != NFLOWS:
+                    short_windows.append((i, int(r["n_registered"])))
             else:
                 r = oracle_host.run_window(backend, win["flows"], win["fx"], win["fy"], win["cx"], win["cy"],
                                            config=CONFIG, boot=boot)
@@ -245,6 +249,8 @@ def bench_reference(args, rank, world):
     }
     if kind != "port":
         line["clocks"] = clk
+        if short_windows:
+            line["note"] = f"windows that registered fewer than {NFLOWS} frames (step, frames): {short_windows}"
     print(json.dumps(line))
 
 
