@@ -446,8 +446,10 @@ __global__ void __launch_bounds__(128)
 // Cooperative candidate cost: the N flow terms and N_dp prior terms of ONE candidate are evaluated by a group
 // of G lanes (one term per lane: the texture fetch and the ~600-instruction Fisk posterior run in parallel),
 // then combined in the reference's order f = 0..N-1, priors 0..N_dp-1 with the same fused multiply-adds, so
-// the result is bit-identical to pixel_cost().  Every lane walks the (cheap) pose chain because the fetch
-// position of frame f depends on the in-view tests of all earlier frames (stale px1 rule).
+// the result is bit-identical to pixel_cost().  The fetch position of frame f depends on the in-view tests of all
+// earlier frames (stale px1 rule): either every lane walks the whole pose chain for itself (SHARE =
+// false, shortest dependent path — small launches), or the lanes share the projections and settle the rule with two
+// ballots (SHARE = true, a fifth fewer instructions — launches that fill the GPU; see launch_local_group).
 // The result is returned on every lane of the group.
 // ------------------------------------------------------------------------------------------------
 template <int G, int TPL, bool SHARE>
