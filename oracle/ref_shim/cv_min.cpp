@@ -214,3 +214,48 @@ int waitKey(int) { return -1; }
 void destroyAllWindows() {}
 
 }  // namespace cv
+
+// ---- self-description of the stand-in's Mat semantics for tests/test_cpu_reference_host.py: the handful of OpenCV
+// behaviours the reference's host code leans on (views write through, headers are shallow, clone is deep, at<T>(i, j)
+// indexes in units of T, the comma initialiser fills row-major, K.inv(), small products, scalar assignment in place).
+extern "C" int cvmin_selftest(double* out) {
+    using namespace cv;
+    int k = 0;
+    Mat pool(4, 6, CV_32F);
+    for (int i = 0; i < 24; i++) pool.at<float>(i / 6, i % 6) = (float)i;
+    Mat alias = pool;                      // shallow
+    Mat copy = pool.clone();               // deep
+    pool.colRange(0, 3) *= 2.0;            // writes through the view (geometry.cpp:187)
+    out[k++] = alias.at<float>(1, 2);      // 16: doubled through the alias
+    out[k++] = alias.at<float>(1, 3);      // 9: outside the column range
+    out[k++] = copy.at<float>(1, 2);       // 8: the clone kept the old value
+    pool.at<Vec3f>(2, 1) = Vec3f(-1, -2, -3);  // second Vec3f of row 2 = columns 3..5 (geometry.cpp:160)
+    out[k++] = pool.at<float>(2, 3), out[k++] = pool.at<float>(2, 5);
+    Mat head = pool.rowRange(0, 2);        // geometry.cpp:176
+    out[k++] = head.rows, out[k++] = head.at<float>(1, 5);
+    Mat row(1, 6, CV_32F);
+    row.at<Vec3f>(1) = Vec3f(7, 8, 9);     // single index on a row vector, in units of Vec3f (geometry.cpp:181)
+    out[k++] = row.at<float>(0, 3), out[k++] = row.at<float>(0, 5);
+    Mat t = Mat::zeros(3, 1, CV_32F);
+    t.at<Vec3f>(0) = Vec3f(1, 2, 3);       // voldor.cpp:64
+    out[k++] = t.at<float>(2);
+    Mat K = (Mat_<float>(3, 3) << 500, 0, 320, 0, 510, 240, 0, 0, 1);
+    out[k++] = K.at<float>(1, 2);          // 240: row-major fill
+    Mat Ki = K.inv();
+    Mat I = K * Ki;
+    out[k++] = Ki.at<float>(0, 0), out[k++] = Ki.at<float>(0, 2), out[k++] = I.at<float>(0, 0) + I.at<float>(1, 1) + I.at<float>(2, 2);
+    Mat c = Mat::ones(2, 2, CV_32F);
+    Mat c2 = c;
+    c = 0;                                 // in place: the second header sees it (geometry.cpp:204)
+    out[k++] = c2.at<float>(1, 1);
+    Mat d64 = Mat::eye(3, 3, CV_64F);
+    d64.convertTo(d64, CV_32F);            // geometry.cpp:329
+    out[k++] = d64.type() == CV_32F ? d64.at<float>(2, 2) : -1;
+    Mat s = Mat::ones(3, 2, CV_32F);
+    out[k++] = sum(s)[0], out[k++] = norm(s), out[k++] = checkRange(s) ? 1 : 0;
+    s.at<float>(2, 1) = NAN;
+    out[k++] = checkRange(s) ? 1 : 0;
+    Mat q = 10.0 / Mat::zeros(1, 2, CV_32F);  // s / m is 0 where m is 0 (voldor.cpp:33 on missing disparities)
+    out[k++] = q.at<float>(0, 1);
+    return k;
+}

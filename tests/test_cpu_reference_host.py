@@ -121,3 +121,20 @@ def test_partial_truncation_reference_host_equals_restatement():
     mine = oracle_host.run_window(kb, *args, config=cfg, boot=boot)
     assert ref["n_registered"] == 3
     _same(mine, ref, "partial truncation")
+
+
+def test_opencv_stand_in_semantics():
+    """the OpenCV behaviours the reference's host code relies on, as implemented by oracle/ref_shim/cv_min: views
+    write through, copies of a header are shallow, clone is deep, at<T>() indexes in units of T, row-major comma
+    initialiser, 3x3 inverse, scalar assignment in place, type conversion, reductions, s / 0 = 0"""
+    import ctypes as C
+
+    L = oracle_host.ref_host_lib()
+    L.cvmin_selftest.restype = C.c_int
+    out = np.zeros(32, np.float64)
+    n = L.cvmin_selftest(out.ctypes.data_as(C.POINTER(C.c_double)))
+    K = np.array([[500, 0, 320], [0, 510, 240], [0, 0, 1]], np.float64)
+    Ki = np.linalg.inv(K)
+    want = [16, 9, 8, -1, -3, 2, 11, 7, 9, 3, 240, Ki[0, 0], Ki[0, 2], 3, 0, 1, 6, np.sqrt(6), 1, 0, 0]
+    assert n == len(want)
+    assert np.allclose(out[:n], want, rtol=1e-6, atol=1e-7), (out[:n], want)
