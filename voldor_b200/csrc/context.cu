@@ -10,8 +10,8 @@ namespace vb {
 namespace {
 // Several execution contexts with two streams each share the device's hardware work queues; with the default of 8 the
 // streams of more than 6 contexts alias and serialise behind each other (measured with 32: +2 % EM-iterations/s at 8 and
-// 12 windows in flight, no change at 6).  Read by the driver when the CUDA context is created, so it only takes effect when this library is loaded
-// before that; a value set by the user wins.
+// 12 windows in flight, no change at 6).  Read by the driver when the CUDA context is created, so it only takes effect
+// when this library is loaded before that; a value set by the user wins.
 __attribute__((constructor)) void default_work_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
 std::atomic<int> g_device{-1};
 std::mutex g_registry_mutex;
